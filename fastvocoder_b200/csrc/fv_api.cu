@@ -1,0 +1,572 @@
+// C ABI of fastvocoder_b200 (see include/fastvocoder_b200.h) + the host-side executor that walks the
+// layer graph of fv_model.h and launches the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fastvocoder_b200.h"
+#include "fv_kernels.cuh"
+#include "fv_model.h"
+#include "fv_tc.cuh"
+
+namespace fv {
+std::atomic<long long> g_launches{0};
+thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define FV_CUDA(expr)                                                                             \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fv::fail(FV_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                      __LINE__);                                                                  \
+  } while (0)
+
+static inline int grid_for(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+}  // namespace fv
+
+struct fv_handle {
+  fv::Model model;
+  const float* packed = nullptr;  // caller-owned canonical weights
+  float* derived = nullptr;       // library-owned kernel-side images (fp32)
+  fv::TcWeights tc;               // library-owned fp16 hi/lo images for the tcgen05 path
+  const float* pqmf_ana = nullptr;
+  const float* pqmf_syn = nullptr;
+  bool bound = false;
+};
+
+namespace fv {
+
+// ---- weight derivation ----------------------------------------------------------------------------
+static int derive_layer(const Layer& l, const float* w_canon, float* wd, cudaStream_t st) {
+  const long long n = (long long)l.Cin * l.Kd * l.N;
+  const int g = grid_for(n);
+  if (l.type == L_CONV) derive_conv_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cout, l.Cin, l.K);
+  else if (l.type == L_CONVT) derive_convt_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cin, l.Cout, l.K, l.stride, l.Kd);
+  else derive_basis_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cout, l.Cin);
+  g_launches++;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
+// ---- one layer ---------------------------------------------------------------------------------------
+struct LayerCall {
+  const float* x = nullptr;
+  float* y = nullptr;
+  const float* res = nullptr;
+  int B = 0;
+  long long Lin = 0;
+  float pre_slope = -1.f;
+  int pad_mode = PAD_ZERO;
+  int acc_mode = ACC_STORE;
+  float acc_div = 1.f;
+  int post_tanh = 0;
+  long long x_bs = -1, y_bs = -1, res_bs = -1;  // -1: dense
+  bool allow_tc = true;
+};
+
+static long long layer_out_len(const Layer& l, long long Lin) {
+  if (l.type == L_CONV) return Lin;
+  if (l.type == L_CONVT) return Model::convt_out_len(l, Lin);
+  return (Lin + 1) * l.N;  // basis: samples
+}
+
+static int run_layer(const Layer& l, const float* wd, const float* bias, const TcLayer* tcl, const LayerCall& c,
+                     cudaStream_t st) {
+  ConvArgs a{};
+  a.x = c.x; a.w = wd; a.bias = bias; a.res = c.res; a.y = c.y;
+  a.B = c.B; a.Cin = l.Cin; a.N = l.N; a.Lin = (int)c.Lin; a.K = l.Kd; a.dil = l.dil;
+  a.pad_mode = c.pad_mode; a.pre_slope = c.pre_slope;
+  a.acc_mode = c.acc_mode; a.acc_div = c.acc_div; a.post_tanh = c.post_tanh;
+  a.x_bs = c.x_bs >= 0 ? c.x_bs : (long long)l.Cin * c.Lin;
+  long long out_per_b;
+  if (l.type == L_CONV) {
+    a.Lpos = (int)c.Lin;
+    a.pad_left = (l.K - 1) * l.dil / 2;  // get_padding (modules.py:186) == ReflectionPad1d((k-1)//2*d)
+    a.out_layout = OUT_BCL;
+    a.bias_mod = l.Cout;
+    out_per_b = (long long)l.Cout * c.Lin;
+  } else if (l.type == L_CONVT) {
+    const long long Lout = Model::convt_out_len(l, c.Lin);
+    a.Lpos = (int)((Lout - 1 + l.padding) / l.stride + 1);
+    a.pad_left = l.Kd - 1;
+    a.out_layout = OUT_PHASE;
+    a.ph_stride = l.stride; a.ph_pad = l.padding; a.ph_cout = l.Cout; a.ph_lout = (int)Lout;
+    a.bias_mod = l.Cout;
+    out_per_b = (long long)l.Cout * Lout;
+  } else {
+    a.Lpos = (int)c.Lin + 1;
+    a.pad_left = 1;
+    a.out_layout = OUT_BLC;
+    a.bias_mod = l.N;
+    out_per_b = (long long)a.Lpos * l.N;
+  }
+  a.y_bs = c.y_bs >= 0 ? c.y_bs : out_per_b;
+  a.res_bs = c.res_bs >= 0 ? c.res_bs : out_per_b;
+  if (c.Lin <= 0 || c.B <= 0) return fail(FV_EINVAL, "empty batch or sequence");
+  if (c.pad_mode == PAD_REFLECT && a.pad_left >= c.Lin)
+    return fail(FV_EINVAL, "ReflectionPad1d needs pad (%d) < length (%lld)", a.pad_left, c.Lin);
+  if (c.allow_tc && tcl && tcl->eligible) {
+    int rc = launch_conv_tc(a, *tcl, st);
+    if (rc == 0) return FV_OK;
+    if (rc < 0) return fail(FV_ECUDA, "tcgen05 conv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // rc > 0: shape not handled by the tensor-core kernel -> exact fp32 kernel (same GPU, not a CPU fallback)
+  }
+  FV_CUDA(launch_conv_ffma(a, st));
+  return FV_OK;
+}
+
+// ---- whole-model forward ----------------------------------------------------------------------------
+struct Bufs {
+  float *a, *b, *h, *u0, *u1, *mel_ext;
+  size_t each_floats;
+};
+
+static size_t max_act_floats(const Model& m, int B, int T) {
+  size_t mx = (size_t)B * m.cfg.channels[0] * T;
+  for (size_t s = 0; s < m.stages.size(); ++s) {
+    size_t v = (size_t)B * m.stages[s].Cout * (size_t)m.len_after(T, (int)s);
+    if (v > mx) mx = v;
+  }
+  if (m.basis >= 0) {
+    size_t v = (size_t)B * (size_t)((m.len_after(T, (int)m.stages.size() - 1) + 1) * (m.cfg.basis_L / 2));
+    if (v > mx) mx = v;
+  }
+  return (mx + 63) / 64 * 64;
+}
+
+static int eff_batch(const Model& m, int B, int flags) {
+  return (m.cfg.kind == FV_BASIS_MELGAN && !(flags & FV_FWD_BASIS_INFERENCE)) ? B + 1 : B;
+}
+
+static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* ws,
+                        size_t ws_bytes, int flags, cudaStream_t st) {
+  const Model& m = h->model;
+  const fv_config& c = m.cfg;
+  const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES);
+  const int Be = eff_batch(m, B, flags);
+  const size_t each = max_act_floats(m, Be, T);
+  const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
+  const size_t need = (5 * each + mel_ext_floats) * sizeof(float);
+  if (ws_bytes < need) return fail(FV_ENOMEM, "workspace too small: have %zu need %zu", ws_bytes, need);
+  float* base = (float*)ws;
+  float* bufA = base;
+  float* bufB = base + each;
+  float* bufH = base + 2 * each;
+  float* bufU0 = base + 3 * each;
+  float* bufU1 = base + 4 * each;
+  float* mel_ext = base + 5 * each;
+
+  auto wd = [&](int li) { return h->derived + m.layers[li].wd_offset; };
+  auto bias = [&](int li) -> const float* {
+    return m.layers[li].b_param >= 0 ? h->packed + m.params[m.layers[li].b_param].offset : nullptr;
+  };
+  auto tcl = [&](int li) -> const TcLayer* { return h->tc.layer(li); };
+  auto call = [&](int li, LayerCall lc) {
+    lc.allow_tc = tc_ok;
+    return run_layer(m.layers[li], wd(li), bias(li), tcl(li), lc, st);
+  };
+
+  const float* x_in = mel;
+  if (Be != B) {  // Basis forward(): append the all-zero utterance (basis_melgan.py:148-151)
+    const long long n = (long long)B * c.in_channels * T;
+    copy_rows_kernel<<<grid_for(n), 256, 0, st>>>(mel, mel_ext, n);
+    g_launches++;
+    FV_CUDA(cudaMemsetAsync(mel_ext + n, 0, (size_t)c.in_channels * T * sizeof(float), st));
+    x_in = mel_ext;
+  }
+
+  int rc;
+  long long L = T;
+  float* cur = bufA;
+  float* other = bufB;
+  {  // conv_pre (hifigan.py:93, zero pad) / ReflectionPad1d + Conv1d (melgan.py:68-71)
+    LayerCall lc;
+    lc.x = x_in; lc.y = cur; lc.B = Be; lc.Lin = L;
+    lc.pad_mode = m.is_hifi() ? PAD_ZERO : PAD_REFLECT;
+    if ((rc = call(m.pre, lc))) return rc;
+  }
+  for (size_t s = 0; s < m.stages.size(); ++s) {
+    const Stage& sg = m.stages[s];
+    {  // LeakyReLU + ConvTranspose1d
+      LayerCall lc;
+      lc.x = cur; lc.y = other; lc.B = Be; lc.Lin = L;
+      lc.pre_slope = m.is_hifi() ? 0.1f : 0.2f;  // LRELU_SLOPE modules.py:9 / negative_slope 0.2 melgan.py:30
+      if ((rc = call(sg.up, lc))) return rc;
+      L = Model::convt_out_len(m.layers[sg.up], L);
+    }
+    std::swap(cur, other);  // cur = upsampled y, other is free
+    if (m.is_hifi()) {
+      // MRF: xs = sum_j resblock_j(y); x = xs / num_kernels (hifigan.py:97-103).  `other` accumulates xs.
+      const int nb = (int)sg.branches.size();
+      for (int j = 0; j < nb; ++j) {
+        const Branch& br = sg.branches[j];
+        const float* bc = cur;
+        const int nu = (int)br.units.size();
+        for (int u = 0; u < nu; ++u) {
+          const bool last = (u == nu - 1);
+          float* dst = last ? other : (u % 2 ? bufU1 : bufU0);
+          int acc = ACC_STORE;
+          float div = 1.f;
+          if (last && j > 0) { acc = (j == nb - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb; }
+          if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
+            LayerCall l1;
+            l1.x = bc; l1.y = bufH; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.1f;
+            if ((rc = call(br.units[u].c1, l1))) return rc;
+            LayerCall l2;
+            l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = Be; l2.Lin = L; l2.pre_slope = 0.1f;
+            l2.acc_mode = acc; l2.acc_div = div;
+            if ((rc = call(br.units[u].c2, l2))) return rc;
+          } else {  // ResBlock2 unit (modules.py:248-251)
+            LayerCall l1;
+            l1.x = bc; l1.y = dst; l1.res = bc; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.1f;
+            l1.acc_mode = acc; l1.acc_div = div;
+            if ((rc = call(br.units[u].c1, l1))) return rc;
+          }
+          bc = dst;
+        }
+      }
+      if (nb == 1) {  // xs / 1: nothing to do
+      }
+      std::swap(cur, other);  // cur = xs/num_kernels
+    } else {
+      for (const Stack& sk : sg.stacks) {  // ResidualStack (modules.py:372-382)
+        LayerCall l1;
+        l1.x = cur; l1.y = bufH; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT;
+        if ((rc = call(sk.dil_conv, l1))) return rc;
+        LayerCall ls;
+        ls.x = cur; ls.y = bufU0; ls.B = Be; ls.Lin = L;
+        if ((rc = call(sk.skip, ls))) return rc;
+        LayerCall l2;
+        l2.x = bufH; l2.y = other; l2.res = bufU0; l2.B = Be; l2.Lin = L; l2.pre_slope = 0.2f;
+        if ((rc = call(sk.conv1x1, l2))) return rc;
+        std::swap(cur, other);
+      }
+    }
+  }
+
+  if (m.is_hifi()) {  // F.leaky_relu(x) [slope 0.01!] -> conv_post -> tanh (hifigan.py:104-106)
+    LayerCall lc;
+    lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = 0.01f; lc.post_tanh = 1;
+    if ((rc = call(m.post, lc))) return rc;
+    if (c.kind == FV_MB_HIFIGAN && out2) {
+      if (!h->pqmf_syn) return fail(FV_ESTATE, "PQMF synthesis filter not bound");
+      const int S = c.pqmf_subbands;
+      dim3 grid(grid_for(L * S), B);
+      pqmf_synthesis_kernel<<<grid, 256, S * (c.pqmf_taps + 1) * sizeof(float), st>>>(out, h->pqmf_syn, out2, S,
+                                                                                     c.pqmf_taps, (int)L);
+      g_launches++;
+      FV_CUDA(cudaGetLastError());
+    }
+  } else if (c.kind == FV_MELGAN) {  // LastLayer (modules.py:85-89) + Tanh (melgan.py:109-110)
+    LayerCall lc;
+    lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = 0.2f; lc.pad_mode = PAD_REFLECT;
+    lc.post_tanh = c.use_final_activation ? 1 : 0;
+    if ((rc = call(m.post, lc))) return rc;
+  } else {  // ReLU -> Linear(C->L) -> overlap_and_add(L/2)  (basis_melgan.py:121, modules.py:264-267)
+    const Layer& bl = m.layers[m.basis];
+    const long long full_len = (L + 1) * bl.N;
+    LayerCall lc;
+    lc.x = cur; lc.B = Be; lc.Lin = L; lc.pre_slope = c.use_final_activation ? 0.f : -1.f;
+    if (flags & FV_FWD_BASIS_INFERENCE) {
+      lc.y = out;
+      if ((rc = call(m.basis, lc))) return rc;
+    } else {
+      lc.y = other;
+      if ((rc = call(m.basis, lc))) return rc;
+      const long long trunc = L * bl.N;  // [:, :weight.size(1) * (L // 2)]
+      dim3 grid(grid_for(trunc), B);
+      sub_broadcast_kernel<<<grid, 256, 0, st>>>(other, other + (long long)B * full_len, out, full_len, trunc);
+      g_launches++;
+      FV_CUDA(cudaGetLastError());
+      if (out2) {
+        const int C = bl.Cin;
+        dim3 g2((unsigned)((L + 31) / 32), (C + 31) / 32, B), b2(32, 8);
+        relu_transpose_sub_kernel<<<g2, b2, 0, st>>>(cur, cur + (long long)B * C * L, out2, C, L);
+        g_launches++;
+        FV_CUDA(cudaGetLastError());
+      }
+    }
+  }
+  return FV_OK;
+}
+
+// temp derived weights for the per-op test entry points
+struct TempW {
+  float* p = nullptr;
+  ~TempW() { if (p) cudaFree(p); }
+  int make(const Layer& l, const float* w, cudaStream_t st) {
+    FV_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)l.Cin * l.Kd * l.N));
+    return derive_layer(l, w, p, st);
+  }
+};
+
+static Layer make_conv_layer(int Cin, int Cout, int K, int dil) {
+  Layer l;
+  l.type = L_CONV; l.Cin = Cin; l.Cout = Cout; l.K = K; l.dil = dil; l.N = Cout; l.Kd = K;
+  return l;
+}
+
+// run one conv with raw canonical weights (test entry points); derives fp32 (and, if asked, fp16 hi/lo) images
+static int conv_raw(const Layer& l, const float* w, const float* bias, const LayerCall& lc, int use_tc,
+                    cudaStream_t st) {
+  TempW tw;
+  int rc = tw.make(l, w, st);
+  if (rc) return rc;
+  TcWeights tcw;
+  const TcLayer* tl = nullptr;
+  if (use_tc) {
+    std::vector<Layer> one{l};
+    one[0].wd_offset = 0;
+    if ((rc = tcw.build(one, tw.p, st))) return fail(FV_ECUDA, "tc weight build failed");
+    tl = tcw.layer(0);
+  }
+  LayerCall c2 = lc;
+  c2.allow_tc = use_tc != 0;
+  rc = run_layer(l, tw.p, bias, tl, c2, st);
+  if (rc) return rc;
+  FV_CUDA(cudaStreamSynchronize(st));  // temp weights are freed on return
+  return FV_OK;
+}
+
+}  // namespace fv
+
+using namespace fv;
+
+extern "C" {
+
+const char* fv_last_error(void) { return g_err.c_str(); }
+int fv_abi_version(void) { return FV_ABI_VERSION; }
+int64_t fv_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int fv_create(const fv_config* cfg, fv_handle** out) {
+  if (!cfg || !out) return fail(FV_EINVAL, "null argument");
+  fv_handle* h = new fv_handle();
+  if (!h->model.build(*cfg)) {
+    int rc = fail(FV_EINVAL, "%s", h->model.err.c_str());
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return FV_OK;
+}
+
+void fv_destroy(fv_handle* h) {
+  if (!h) return;
+  if (h->derived) cudaFree(h->derived);
+  h->tc.release();
+  delete h;
+}
+
+int fv_num_params(const fv_handle* h) { return h ? (int)h->model.params.size() : FV_EINVAL; }
+
+int fv_param_info(const fv_handle* h, int index, char* name, int name_cap, int64_t shape[4], int* ndim,
+                  int64_t* offset_floats) {
+  if (!h || index < 0 || index >= (int)h->model.params.size()) return fail(FV_EINVAL, "bad param index");
+  const Param& p = h->model.params[index];
+  if (name && name_cap > 0) {
+    strncpy(name, p.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
+  if (ndim) *ndim = p.ndim;
+  if (offset_floats) *offset_floats = p.offset;
+  return FV_OK;
+}
+
+int64_t fv_param_total_floats(const fv_handle* h) { return h ? h->model.total_floats : FV_EINVAL; }
+
+int fv_bind_weights(fv_handle* h, const float* packed_dev, int64_t n_floats, const float* pqmf_analysis_dev,
+                    const float* pqmf_synthesis_dev, void* stream) {
+  if (!h || !packed_dev) return fail(FV_EINVAL, "null argument");
+  if (n_floats < h->model.total_floats)
+    return fail(FV_EINVAL, "packed weights too short: %lld < %lld", (long long)n_floats,
+                (long long)h->model.total_floats);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->derived) { cudaFree(h->derived); h->derived = nullptr; }
+  h->tc.release();
+  FV_CUDA(cudaMalloc(&h->derived, sizeof(float) * (size_t)h->model.derived_floats));
+  for (const Layer& l : h->model.layers) {
+    int rc = derive_layer(l, packed_dev + h->model.params[l.w_param].offset, h->derived + l.wd_offset, st);
+    if (rc) return rc;
+  }
+  if (h->tc.build(h->model.layers, h->derived, st)) return fail(FV_ECUDA, "tensor-core weight image build failed");
+  h->packed = packed_dev;
+  h->pqmf_ana = pqmf_analysis_dev;
+  h->pqmf_syn = pqmf_synthesis_dev;
+  FV_CUDA(cudaStreamSynchronize(st));
+  h->bound = true;
+  return FV_OK;
+}
+
+int fv_out_length(const fv_handle* h, int T, int flags, int64_t* out_len) {
+  if (!h || !out_len || T <= 0) return fail(FV_EINVAL, "bad argument");
+  *out_len = h->model.out_length(T, flags);
+  return FV_OK;
+}
+
+int fv_workspace_bytes(const fv_handle* h, int B, int T, size_t* bytes) {
+  if (!h || !bytes || B <= 0 || T <= 0) return fail(FV_EINVAL, "bad argument");
+  const int Be = h->model.cfg.kind == FV_BASIS_MELGAN ? B + 1 : B;
+  const size_t each = max_act_floats(h->model, Be, T);
+  const size_t mel_ext = ((size_t)Be * h->model.cfg.in_channels * T + 63) / 64 * 64;
+  *bytes = (5 * each + mel_ext) * sizeof(float);
+  return FV_OK;
+}
+
+int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,
+               size_t workspace_bytes, int flags, void* stream) {
+  if (!h || !mel || !out || !workspace) return fail(FV_EINVAL, "null argument");
+  if (!h->bound) return fail(FV_ESTATE, "fv_forward before fv_bind_weights");
+  if (B <= 0 || T <= 0) return fail(FV_EINVAL, "B and T must be > 0");
+  if (!h->model.is_hifi() && T <= (h->model.cfg.pre_kernel_size - 1) / 2)
+    return fail(FV_EINVAL, "ReflectionPad1d needs T > %d", (h->model.cfg.pre_kernel_size - 1) / 2);
+  if (h->model.out_length(T, flags) <= 0) return fail(FV_EINVAL, "T too small for this architecture");
+  return forward_impl(h, mel, B, T, out, out2, workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops) {
+  if (!h || !flops) return fail(FV_EINVAL, "null argument");
+  *flops = 2.0 * h->model.macs_per_utt(T) * eff_batch(h->model, B, flags);
+  return FV_OK;
+}
+
+int fv_conv1d(const float* x, const float* w, const float* bias, const float* residual, float* y, int B, int Cin,
+              int Cout, int L, int K, int dilation, int pad_mode, float pre_slope, int post_tanh, int use_tc,
+              void* stream) {
+  if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || L <= 0 || K <= 0 || K % 2 == 0 || dilation <= 0)
+    return fail(FV_EINVAL, "fv_conv1d: bad argument (K must be odd: 'same' convolution)");
+  Layer l = make_conv_layer(Cin, Cout, K, dilation);
+  LayerCall lc;
+  lc.x = x; lc.y = y; lc.res = residual; lc.B = B; lc.Lin = L;
+  lc.pre_slope = pre_slope; lc.pad_mode = pad_mode; lc.post_tanh = post_tanh;
+  return conv_raw(l, w, bias, lc, use_tc, (cudaStream_t)stream);
+}
+
+int fv_conv_transpose1d(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                        int Lin, int K, int stride, int padding, int output_padding, float pre_slope, int use_tc,
+                        void* stream) {
+  if (!x || !w || !y || B <= 0 || Cin <= 0 || Cout <= 0 || Lin <= 0 || K <= 0 || stride <= 0 || K < stride)
+    return fail(FV_EINVAL, "fv_conv_transpose1d: bad argument");
+  Layer l;
+  l.type = L_CONVT; l.Cin = Cin; l.Cout = Cout; l.K = K; l.dil = 1;
+  l.stride = stride; l.padding = padding; l.output_padding = output_padding;
+  l.N = stride * Cout; l.Kd = (K + stride - 1) / stride;
+  if (Model::convt_out_len(l, Lin) <= 0) return fail(FV_EINVAL, "fv_conv_transpose1d: empty output");
+  LayerCall lc;
+  lc.x = x; lc.y = y; lc.B = B; lc.Lin = Lin; lc.pre_slope = pre_slope;
+  return conv_raw(l, w, bias, lc, use_tc, (cudaStream_t)stream);
+}
+
+int fv_resblock1(const float* x, const float* const* w1, const float* const* b1, const float* const* w2,
+                 const float* const* b2, const int* dilations, int num_dilations, float* y, float* scratch,
+                 int B, int C, int L, int K, int use_tc, void* stream) {
+  if (!x || !y || !scratch || num_dilations <= 0) return fail(FV_EINVAL, "fv_resblock1: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hbuf = scratch;                          // [B,C,L]
+  float* pp[2] = {scratch + (size_t)B * C * L, y};  // ping-pong so the last unit lands in y
+  const float* cur = x;
+  for (int u = 0; u < num_dilations; ++u) {
+    float* dst = pp[(num_dilations - 1 - u) % 2 ? 0 : 1];
+    Layer l1 = make_conv_layer(C, C, K, dilations[u]);
+    LayerCall c1;
+    c1.x = cur; c1.y = hbuf; c1.B = B; c1.Lin = L; c1.pre_slope = 0.1f;
+    int rc = conv_raw(l1, w1[u], b1 ? b1[u] : nullptr, c1, use_tc, st);
+    if (rc) return rc;
+    Layer l2 = make_conv_layer(C, C, K, 1);
+    LayerCall c2;
+    c2.x = hbuf; c2.y = dst; c2.res = cur; c2.B = B; c2.Lin = L; c2.pre_slope = 0.1f;
+    rc = conv_raw(l2, w2[u], b2 ? b2[u] : nullptr, c2, use_tc, st);
+    if (rc) return rc;
+    cur = dst;
+  }
+  return FV_OK;
+}
+
+int fv_residual_stack(const float* c, const float* w_dil, const float* b_dil, const float* w_1x1,
+                      const float* b_1x1, const float* w_skip, const float* b_skip, float* y, float* scratch,
+                      int B, int C, int L, int K, int dilation, int use_tc, void* stream) {
+  if (!c || !y || !scratch) return fail(FV_EINVAL, "fv_residual_stack: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* hbuf = scratch;
+  float* ubuf = scratch + (size_t)B * C * L;
+  Layer ld = make_conv_layer(C, C, K, dilation);
+  LayerCall c1;
+  c1.x = c; c1.y = hbuf; c1.B = B; c1.Lin = L; c1.pre_slope = 0.2f; c1.pad_mode = PAD_REFLECT;
+  int rc = conv_raw(ld, w_dil, b_dil, c1, use_tc, st);
+  if (rc) return rc;
+  Layer l1 = make_conv_layer(C, C, 1, 1);
+  LayerCall cs;
+  cs.x = c; cs.y = ubuf; cs.B = B; cs.Lin = L;
+  if ((rc = conv_raw(l1, w_skip, b_skip, cs, use_tc, st))) return rc;
+  LayerCall c2;
+  c2.x = hbuf; c2.y = y; c2.res = ubuf; c2.B = B; c2.Lin = L; c2.pre_slope = 0.2f;
+  return conv_raw(l1, w_1x1, b_1x1, c2, use_tc, st);
+}
+
+int fv_overlap_add(const float* frames, int B, int num_frames, int frame_length, int frame_step, float* out,
+                   void* stream) {
+  if (!frames || !out || B <= 0 || num_frames <= 0) return fail(FV_EINVAL, "fv_overlap_add: bad argument");
+  if (frame_length != 2 * frame_step) return fail(FV_EINVAL, "fv_overlap_add: only frame_length == 2*frame_step");
+  dim3 grid(grid_for((long long)(num_frames + 1) * frame_step), B);
+  overlap_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, out, num_frames, frame_step);
+  g_launches++;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
+int fv_pqmf_synthesis(const float* x, const float* synthesis_filter, int B, int subbands, int taps, int Lband,
+                      float* y, void* stream) {
+  if (!x || !synthesis_filter || !y || B <= 0 || subbands <= 0 || taps <= 0 || taps % 2 || Lband <= 0)
+    return fail(FV_EINVAL, "fv_pqmf_synthesis: bad argument");
+  dim3 grid(grid_for((long long)Lband * subbands), B);
+  pqmf_synthesis_kernel<<<grid, 256, subbands * (taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      x, synthesis_filter, y, subbands, taps, Lband);
+  g_launches++;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
+int fv_pqmf_analysis(const float* x, const float* analysis_filter, int B, int subbands, int taps, int L, float* y,
+                     void* stream) {
+  if (!x || !analysis_filter || !y || B <= 0 || subbands <= 0 || taps <= 0 || taps % 2 || L < subbands)
+    return fail(FV_EINVAL, "fv_pqmf_analysis: bad argument");
+  const long long Lb = (L - subbands) / subbands + 1;  // conv1d(stride=S, kernel=S) output length
+  dim3 grid(grid_for(Lb), B);
+  pqmf_analysis_kernel<<<grid, 256, subbands * (taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
+      x, analysis_filter, y, subbands, taps, (long long)L, Lb);
+  g_launches++;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
+int fv_encode_16bits(const float* x, int64_t n, float rescale_out, int16_t* out, float* scratch1, void* stream) {
+  if (!x || !out || !scratch1 || n <= 0) return fail(FV_EINVAL, "fv_encode_16bits: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  FV_CUDA(cudaMemsetAsync(scratch1, 0, sizeof(float), st));
+  absmax_kernel<<<grid_for(n), 256, 0, st>>>(x, n, (unsigned int*)scratch1);
+  encode16_kernel<<<grid_for(n), 256, 0, st>>>(x, n, (const unsigned int*)scratch1, rescale_out, (short*)out);
+  g_launches += 2;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// CUDA-core (exact fp32 FFMA) kernels of the generator forward path + small utility kernels.
+// One generic "GEMM conv over time" kernel serves Conv1d, polyphase ConvTranspose1d and the
+// Basis-MelGAN linear+overlap-add (see Layer in fv_model.h for the three views).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+namespace fv {
+
+extern std::atomic<long long> g_launches;
+
+enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
+enum { ACC_STORE = 0, ACC_ADD = 1, ACC_ADD_DIV = 2 };
+enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2 };
+
+struct ConvArgs {
+  const float* x;     // [B, Cin, Lin]
+  const float* w;     // derived image [Cin][K][N]
+  const float* bias;  // [bias_mod] or nullptr
+  const float* res;   // residual, same layout/strides as y, or nullptr
+  float* y;
+  int B, Cin, N, Lin, Lpos, K, dil, pad_left;
+  int pad_mode;     // PAD_ZERO / PAD_REFLECT
+  float pre_slope;  // < 0: no pre-activation; >= 0: leaky_relu(x, slope) (0 = ReLU)
+  int acc_mode;     // ACC_*
+  float acc_div;
+  int post_tanh;
+  int out_layout;   // OUT_*
+  int bias_mod;
+  // OUT_PHASE (ConvTranspose1d): n = r*ph_cout + co ; t = pos*ph_stride + r - ph_pad in [0, ph_lout)
+  int ph_stride, ph_pad, ph_cout, ph_lout;
+  long long x_bs, y_bs, res_bs;  // batch strides in floats
+};
+
+__device__ __forceinline__ float pre_act(float v, float slope) {
+  return (slope >= 0.f && v < 0.f) ? v * slope : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic fp32 conv: CTA tile = CO_T outputs x TT positions, 8 warps, thread tile 8 (n) x 8 (pos).
+// lanes own consecutive positions (conflict-free shared reads, coalesced stores), warps own groups
+// of 8 output channels (weight reads are warp-broadcast LDS.128).
+// ---------------------------------------------------------------------------------------------
+template <int CO_T>
+struct ConvTile {
+  static constexpr int CPT = 8, TPT = 8, CI_C = 8;
+  static constexpr int NWC = CO_T / CPT;       // warps along N
+  static constexpr int NWT = 8 / NWC;          // warps along positions
+  static constexpr int TT = NWT * 32 * TPT;    // positions per CTA
+};
+
+template <int CO_T>
+__global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
+  using T = ConvTile<CO_T>;
+  constexpr int CPT = T::CPT, TPT = T::TPT, CI_C = T::CI_C, NWC = T::NWC, TT = T::TT;
+  extern __shared__ float smem[];
+  const int halo = (a.K - 1) * a.dil;
+  const int XW = TT + halo;
+  float* sx = smem;                 // [CI_C][XW]
+  float* sw = smem + CI_C * XW;     // [CI_C][K][CO_T]
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.y * CO_T;
+  const int t0 = blockIdx.x * TT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wc = warp % NWC, wt = warp / NWC;
+
+  float acc[CPT][TPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i)
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) acc[i][j] = 0.f;
+
+  const float* xb = a.x + (long long)b * a.x_bs;
+  const int wrow = a.K * CO_T;
+
+  for (int ci0 = 0; ci0 < a.Cin; ci0 += CI_C) {
+    {  // x tile: warp `warp` stages channel ci0+warp (CI_C == 8 warps)
+      const int ci = ci0 + warp;
+      float* row = sx + warp * XW;
+      const bool cok = ci < a.Cin;
+      const float* xr = xb + (long long)ci * a.Lin;
+      for (int s = lane; s < XW; s += 32) {
+        int g = t0 - a.pad_left + s;
+        if (a.pad_mode == PAD_REFLECT) {
+          if (g < 0) g = -g;
+          if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+        }
+        float v = 0.f;
+        if (cok && g >= 0 && g < a.Lin) v = pre_act(__ldg(xr + g), a.pre_slope);
+        row[s] = v;
+      }
+    }
+    {  // weight tile rows (c, j) are contiguous in the derived image
+      const int rows = CI_C * a.K;
+      const long long base = (long long)ci0 * a.K;
+      const int rows_ok = (a.Cin - ci0) * a.K;  // rows beyond Cin are zero
+      for (int idx = threadIdx.x; idx < rows * CO_T; idx += 256) {
+        const int r = idx / CO_T, co = idx - r * CO_T;
+        float v = 0.f;
+        if (r < rows_ok && n0 + co < a.N) v = __ldg(a.w + (base + r) * a.N + n0 + co);
+        sw[idx] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int c = 0; c < CI_C; ++c) {
+      const float* sxr = sx + c * XW + wt * (32 * TPT) + lane;
+      const float* swr = sw + c * wrow + wc * CPT;
+#pragma unroll 1
+      for (int j = 0; j < a.K; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(swr + j * CO_T);
+        const float4 w1 = *reinterpret_cast<const float4*>(swr + j * CO_T + 4);
+        const float wv[CPT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float xv[TPT];
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) xv[i] = sxr[j * a.dil + 32 * i];
+#pragma unroll
+        for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+          for (int i = 0; i < TPT; ++i) acc[cc][i] = fmaf(wv[cc], xv[i], acc[cc][i]);
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: bias, residual, MRF accumulate, tanh, layout
+  float* yb = a.y + (long long)b * a.y_bs;
+  const float* rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
+#pragma unroll
+  for (int cc = 0; cc < CPT; ++cc) {
+    const int n = n0 + wc * CPT + cc;
+    if (n >= a.N) break;
+    const float bv = a.bias ? __ldg(a.bias + (n % a.bias_mod)) : 0.f;
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int pos = t0 + wt * (32 * TPT) + lane + 32 * i;
+      if (pos >= a.Lpos) continue;
+      long long o;
+      if (a.out_layout == OUT_BCL) {
+        o = (long long)n * a.Lpos + pos;
+      } else if (a.out_layout == OUT_BLC) {
+        o = (long long)pos * a.N + n;
+      } else {
+        const int r = n / a.ph_cout, co = n - r * a.ph_cout;
+        const int t = pos * a.ph_stride + r - a.ph_pad;
+        if (t < 0 || t >= a.ph_lout) continue;
+        o = (long long)co * a.ph_lout + t;
+      }
+      float v = acc[cc][i] + bv;
+      if (rb) v += rb[o];
+      if (a.acc_mode == ACC_ADD) v = yb[o] + v;
+      else if (a.acc_mode == ACC_ADD_DIV) v = (yb[o] + v) / a.acc_div;
+      if (a.post_tanh) v = tanhf(v);
+      yb[o] = v;
+    }
+  }
+}
+
+inline size_t conv_ffma_smem(int co_t, int K, int dil) {
+  int tt = (co_t == 16) ? ConvTile<16>::TT : (co_t == 32) ? ConvTile<32>::TT : ConvTile<64>::TT;
+  return (size_t)(8 * (tt + (K - 1) * dil) + 8 * K * co_t) * sizeof(float);
+}
+
+inline cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t st) {
+  const int co_t = a.N <= 16 ? 16 : (a.N <= 32 ? 32 : 64);
+  const size_t smem = conv_ffma_smem(co_t, a.K, a.dil);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  dim3 block(256);
+#define FV_LAUNCH(COT)                                                                              \
+  {                                                                                                 \
+    dim3 grid((a.Lpos + ConvTile<COT>::TT - 1) / ConvTile<COT>::TT, (a.N + COT - 1) / COT, a.B);    \
+    if (smem > 48 * 1024) {                                                                         \
+      e = cudaFuncSetAttribute(conv_ffma_kernel<COT>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                               (int)smem);                                                          \
+      if (e != cudaSuccess) return e;                                                               \
+    }                                                                                               \
+    conv_ffma_kernel<COT><<<grid, block, smem, st>>>(a);                                            \
+  }
+  if (co_t == 16) FV_LAUNCH(16) else if (co_t == 32) FV_LAUNCH(32) else FV_LAUNCH(64)
+#undef FV_LAUNCH
+  g_launches++;
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight image derivation (bind time)
+// ---------------------------------------------------------------------------------------------
+// Conv1d [Cout][Cin][K] -> [Cin][K][Cout]
+__global__ void derive_conv_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cout, int Cin, int K) {
+  const long long n = (long long)Cout * Cin * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long r = i / Cout;
+    const int j = (int)(r % K);
+    const int ci = (int)(r / K);
+    wd[i] = w[((long long)co * Cin + ci) * K + j];
+  }
+}
+// ConvTranspose1d [Cin][Cout][K] -> [Cin][M][stride*Cout], tap m' <-> input offset pos-(M-1)+m' <-> kk = r + (M-1-m')*stride
+__global__ void derive_convt_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cin, int Cout, int K,
+                                    int stride, int M) {
+  const int N = stride * Cout;
+  const long long n = (long long)Cin * M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int nn = (int)(i % N);
+    const long long q = i / N;
+    const int mp = (int)(q % M);
+    const int ci = (int)(q / M);
+    const int r = nn / Cout, co = nn - r * Cout;
+    const int kk = r + (M - 1 - mp) * stride;
+    wd[i] = kk < K ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
+  }
+}
+// Basis Linear [L][C] -> [C][2][hop]: tap 0 <-> frame n-1 second half (rows hop..L-1), tap 1 <-> frame n first half
+__global__ void derive_basis_kernel(const float* __restrict__ w, float* __restrict__ wd, int L, int C) {
+  const int hop = L / 2;
+  const long long n = (long long)C * 2 * hop;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % hop);
+    const long long q = i / hop;
+    const int j = (int)(q % 2);
+    const int ci = (int)(q / 2);
+    wd[i] = w[(long long)((j == 0 ? hop : 0) + co) * C + ci];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PQMF (pqmf.py:108-135).  Index arithmetic is exact: for impulse inputs exactly one product is
+// non-zero per output sample, so results are bit-identical to the reference.
+// synthesis: y[t] = sum_k sum_{j : (t+j-P) % S == 0, 0 <= (t+j-P)/S < Lb} (S*x[k,(t+j-P)/S]) * h[k,j],  P = taps/2
+// ---------------------------------------------------------------------------------------------
+__global__ void pqmf_synthesis_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ y,
+                                      int S, int taps, int Lb) {
+  extern __shared__ float sh[];  // [S][taps+1]
+  const int nt = taps + 1;
+  for (int i = threadIdx.x; i < S * nt; i += blockDim.x) sh[i] = h[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long long L = (long long)Lb * S;
+  const int P = taps / 2;
+  const float scale = (float)S;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
+    // smallest j >= 0 with (t + j - P) % S == 0
+    long long u = t - P;
+    int j0 = (int)(((-u) % S + S) % S);
+    float acc = 0.f;
+    for (int k = 0; k < S; ++k) {
+      const float* xk = x + ((long long)b * S + k) * Lb;
+      const float* hk = sh + k * nt;
+      for (int j = j0; j < nt; j += S) {
+        const long long n = (u + j) / S;
+        if (n >= 0 && n < Lb) acc = fmaf(scale * __ldg(xk + n), hk[j], acc);
+      }
+    }
+    y[(long long)b * L + t] = acc;
+  }
+}
+// analysis: a[k,n] = sum_j xpad[S*n + j] * h[k,j], xpad = zero pad P each side; n < L/S (conv1d stride S floor)
+__global__ void pqmf_analysis_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ y,
+                                     int S, int taps, long long L, long long Lb) {
+  extern __shared__ float sh[];
+  const int nt = taps + 1;
+  for (int i = threadIdx.x; i < S * nt; i += blockDim.x) sh[i] = h[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int P = taps / 2;
+  const float* xb = x + (long long)b * L;
+  for (long long n = blockIdx.x * (long long)blockDim.x + threadIdx.x; n < Lb; n += (long long)gridDim.x * blockDim.x) {
+    for (int k = 0; k < S; ++k) {
+      const float* hk = sh + k * nt;
+      float acc = 0.f;
+      for (int j = 0; j < nt; ++j) {
+        const long long g = n * S + j - P;
+        if (g >= 0 && g < L) acc = fmaf(__ldg(xb + g), hk[j], acc);
+      }
+      y[((long long)b * S + k) * Lb + n] = acc;
+    }
+  }
+}
+
+// overlap_and_add for frame_length == 2*step: out[n*step + j] = f[n][j] + f[n-1][step + j]  (modules.py:34-73)
+__global__ void overlap_add_kernel(const float* __restrict__ f, float* __restrict__ out, int frames, int step) {
+  const int b = blockIdx.y;
+  const long long n_out = (long long)(frames + 1) * step;
+  const float* fb = f + (long long)b * frames * 2 * step;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / step;
+    const int j = (int)(i - n * step);
+    float v = 0.f;
+    if (n >= 1) v += fb[(n - 1) * 2 * step + step + j];  // index_add_ order: frame n-1's second half first
+    if (n < frames) v += fb[n * 2 * step + j];
+    out[(long long)b * n_out + i] = v;
+  }
+}
+
+// Basis forward(): est[b, i] = full[b, i] - full[zero, i], i < Ltrunc (full rows have Lfull samples)
+__global__ void sub_broadcast_kernel(const float* __restrict__ full, const float* __restrict__ zero, float* __restrict__ out,
+                                     long long Lfull, long long Ltrunc) {
+  const int b = blockIdx.y;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Ltrunc; i += (long long)gridDim.x * blockDim.x)
+    out[(long long)b * Ltrunc + i] = full[(long long)b * Lfull + i] - zero[i];
+}
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+// weight[b, l, c] = relu(x[b, c, l]) - relu(x0[c, l])   (basis_melgan.py:154-160)
+__global__ void relu_transpose_sub_kernel(const float* __restrict__ x, const float* __restrict__ x0, float* __restrict__ out,
+                                          int C, long long L) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long l0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* xb = x + (long long)b * C * L;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const long long l = l0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && l < L) {
+      const float a = xb[(long long)c * L + l], z = x0 ? x0[(long long)c * L + l] : 0.f;
+      v = fmaxf(a, 0.f) - (x0 ? fmaxf(z, 0.f) : 0.f);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const long long l = l0 + r;
+    const int c = c0 + threadIdx.x;
+    if (c < C && l < L) out[((long long)b * L + l) * C + c] = tile[threadIdx.x][r];
+  }
+}
+
+// save_wav quantiser (data/audio.py:12-14): peak -> scale -> int16 truncation
+__global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like uints
+}
+__global__ void encode16_kernel(const float* __restrict__ x, long long n, const unsigned int* __restrict__ peak_bits,
+                                float rescale, short* __restrict__ out) {
+  // numpy: x *= 32767 / max(0.01, max|x|) * rescale_out  (python float64 scalar, applied to a float32 array)
+  const double scale = 32767.0 / fmax(0.01, (double)__uint_as_float(*peak_bits)) * (double)rescale;
+  const float s = (float)scale;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (short)(int)(x[i] * s);  // astype(int16): truncation toward zero
+}
+
+}  // namespace fv

@@ -1,0 +1,487 @@
+"""Drop-in generator classes: same constructors (YAML keys), state_dict keys, ``forward`` /
+``inference`` / ``remove_weight_norm`` / ``apply_weight_norm`` as the reference's
+model/generator/{hifigan,multiband_hifigan,melgan,basis_melgan}.py — but the forward path is the
+hand-written sm_100a CUDA of libfastvocoder_b200.so reached through its C ABI.
+
+There is no PyTorch / CPU fallback: ``forward`` on a CPU tensor raises.
+
+Host-side responsibilities kept here (all load-time, none per step):
+  * weight-norm folding ``w = g * v / ||v||`` with ``torch._weight_norm`` — the very function
+    ``torch.nn.utils.remove_weight_norm`` uses (hifigan.py:58-67), so folded weights are bit-identical;
+  * packing every folded parameter into ONE flat fp32 buffer (the unit a multi-GPU launch broadcasts
+    once over NCCL, see sharding.py) at the offsets the C library reports;
+  * allocating outputs / workspace as torch tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .pqmf import PQMF
+
+__all__ = ["HiFiGANGenerator", "MultiBandHiFiGANGenerator", "MelGANGenerator", "BasisMelGANGenerator",
+           "build_generator"]
+
+
+def _set_arr(arr, values):
+    for i, v in enumerate(values):
+        arr[i] = int(v)
+
+
+class _NativeGenerator(torch.nn.Module):
+    """Shared machinery; subclasses fill an FvConfig from their reference-style kwargs."""
+
+    model_name = ""
+
+    def __init__(self, cfg: _lib.FvConfig, use_weight_norm: bool = True):
+        super().__init__()
+        self._cfg = cfg
+        self._handle = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.fv_create(C.byref(cfg), C.byref(self._handle)), "fv_create")
+        self._spec = []  # (name, shape, offset)
+        name_buf = C.create_string_buffer(256)
+        shape = (C.c_int64 * 4)()
+        ndim = C.c_int()
+        off = C.c_int64()
+        for i in range(L.fv_num_params(self._handle)):
+            _lib.check(L.fv_param_info(self._handle, i, name_buf, 256, shape, C.byref(ndim), C.byref(off)))
+            self._spec.append((name_buf.value.decode(), tuple(int(shape[d]) for d in range(ndim.value)),
+                               int(off.value)))
+        total = int(L.fv_param_total_floats(self._handle))
+        self.register_buffer("packed_weights", torch.zeros(total, dtype=torch.float32), persistent=False)
+        self._wn = OrderedDict()      # layer prefix -> (weight_g, weight_v): present while weight norm is applied
+        self._bound_key = None
+        self._workspace = None
+        self.use_tensor_cores = True
+        self._reset_parameters()
+        if use_weight_norm:
+            self.apply_weight_norm()
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.lib().fv_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- parameters --------------------------------------------------------------------------
+    def _view(self, name):
+        for n, shape, off in self._spec:
+            if n == name:
+                return self.packed_weights[off: off + int(np.prod(shape))].view(shape)
+        raise KeyError(name)
+
+    def _wn_layers(self):
+        """Layers the reference wraps in weight norm: every Conv1d / ConvTranspose1d (hifigan.py:69-77)."""
+        return [n[:-len(".weight")] for n, shape, _ in self._spec if n.endswith(".weight") and len(shape) == 3]
+
+    def _reset_parameters(self):
+        """Random init (PyTorch-default-like uniform(+-1/sqrt(fan_in))); real use loads a checkpoint."""
+        with torch.no_grad():
+            for name, shape, _ in self._spec:
+                v = self._view(name)
+                if name.endswith(".bias"):
+                    w_shape = dict((n, s) for n, s, _ in self._spec)[name[:-5] + ".weight"]
+                    bound = 1.0 / math.sqrt(w_shape[1] * w_shape[2])
+                else:
+                    bound = 1.0 / math.sqrt(shape[1] * (shape[2] if len(shape) == 3 else 1))
+                v.uniform_(-bound, bound)
+
+    def apply_weight_norm(self):
+        """Re-parametrise conv weights as (g, v) like torch.nn.utils.weight_norm(dim=0) (hifigan.py:69-77)."""
+        with torch.no_grad():
+            for p in self._wn_layers():
+                w = self._view(p + ".weight").detach().clone()
+                g = torch.norm_except_dim(w, 2, 0)
+                self._wn[p] = (g, w)
+
+    def remove_weight_norm(self):
+        """Fold g*v/||v|| into .weight and drop the re-parametrisation (hifigan.py:58-67)."""
+        self._fold()
+        self._wn.clear()
+
+    def _fold(self):
+        with torch.no_grad():
+            for p, (g, v) in self._wn.items():
+                w = torch._weight_norm(v.float().cpu(), g.float().cpu(), 0)
+                self._view(p + ".weight").copy_(w)
+        self._bound_key = None
+
+    def reset_parameters(self):
+        self._reset_parameters()
+        if self._wn:
+            self.apply_weight_norm()
+        self._bound_key = None
+
+    def state_dict(self, *args, **kwargs):
+        """Reference key set: weight-norm form while it is applied, folded form after remove_weight_norm()."""
+        sd = OrderedDict()
+        for name, shape, _ in self._spec:
+            prefix = name[:-len(".weight")] if name.endswith(".weight") else None
+            if prefix is not None and prefix in self._wn:
+                g, v = self._wn[prefix]
+                sd[prefix + ".weight_g"] = g.detach().clone()
+                sd[prefix + ".weight_v"] = v.detach().clone()
+            else:
+                sd[name] = self._view(name).detach().clone()
+        for k, v in self._extra_state_tensors().items():
+            sd[k] = v.detach().clone()
+        return sd
+
+    def _extra_state_tensors(self):
+        return {}
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Accepts reference checkpoints in either form (``*.weight_g/_v`` or folded ``*.weight``)."""
+        missing, used = [], set()
+        new_wn = OrderedDict()
+        with torch.no_grad():
+            for name, shape, _ in self._spec:
+                prefix = name[:-len(".weight")] if name.endswith(".weight") else None
+                if name in state_dict:
+                    t = torch.as_tensor(state_dict[name]).detach().float().cpu()
+                    if tuple(t.shape) != shape:
+                        raise RuntimeError(f"size mismatch for {name}: checkpoint {tuple(t.shape)} vs model {shape}")
+                    self._view(name).copy_(t)
+                    used.add(name)
+                elif prefix is not None and prefix + ".weight_g" in state_dict and prefix + ".weight_v" in state_dict:
+                    g = torch.as_tensor(state_dict[prefix + ".weight_g"]).detach().float().cpu()
+                    v = torch.as_tensor(state_dict[prefix + ".weight_v"]).detach().float().cpu()
+                    if tuple(v.shape) != shape:
+                        raise RuntimeError(f"size mismatch for {prefix}.weight_v: {tuple(v.shape)} vs {shape}")
+                    new_wn[prefix] = (g, v)
+                    used.update((prefix + ".weight_g", prefix + ".weight_v"))
+                else:
+                    missing.append(name)
+        unexpected = [k for k in state_dict if k not in used and not k.startswith("pqmf.")]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict for {type(self).__name__}: "
+                               f"missing keys {missing}, unexpected keys {unexpected}")
+        self._wn = new_wn
+        self._fold()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    # ---- device binding -------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.packed_weights.device
+
+    def _pqmf_ptrs(self):
+        return None, None
+
+    def _ensure_bound(self):
+        pw = self.packed_weights
+        if not pw.is_cuda:
+            raise _lib.FvError(f"{type(self).__name__}: weights are on {pw.device}; this implementation has no CPU "
+                               "path — call .to('cuda') first")
+        if self._wn and self._bound_key is None:
+            self._fold()
+        key = (pw.data_ptr(), pw._version, pw.device.index)
+        if key != self._bound_key:
+            ana, syn = self._pqmf_ptrs()
+            with torch.cuda.device(pw.device):
+                _lib.check(_lib.lib().fv_bind_weights(self._handle, _lib.ptr(pw), pw.numel(), ana, syn,
+                                                      _lib.current_stream_ptr()), "fv_bind_weights")
+            self._bound_key = key
+
+    def _get_workspace(self, B, T):
+        need = C.c_size_t()
+        _lib.check(_lib.lib().fv_workspace_bytes(self._handle, B, T, C.byref(need)), "fv_workspace_bytes")
+        ws = self._workspace
+        if ws is None or ws.numel() < need.value or ws.device != self.device:
+            self._workspace = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        return ws
+
+    def out_length(self, T: int, flags: int = 0) -> int:
+        n = C.c_int64()
+        _lib.check(_lib.lib().fv_out_length(self._handle, int(T), int(flags), C.byref(n)), "fv_out_length")
+        return int(n.value)
+
+    def forward_flops(self, B: int, T: int, flags: int = 0) -> float:
+        f = C.c_double()
+        _lib.check(_lib.lib().fv_forward_flops(self._handle, int(B), int(T), int(flags), C.byref(f)))
+        return float(f.value)
+
+    def _run(self, x, out, out2, flags=0):
+        B, _, T = x.shape
+        ws = self._get_workspace(B, T)
+        if not self.use_tensor_cores:
+            flags |= _lib.FV_FWD_NO_TENSOR_CORES
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fv_forward(self._handle, _lib.ptr(x), B, T, _lib.ptr(out), _lib.ptr(out2),
+                                             _lib.ptr(ws), ws.numel(), flags, _lib.current_stream_ptr()),
+                       "fv_forward")
+
+    def _prep_input(self, x):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("forward expects a torch.Tensor [B, in_channels, T]")
+        self._ensure_bound()
+        if x.device != self.device:
+            raise _lib.FvError(f"input on {x.device} but model on {self.device} (no CPU fallback)")
+        if x.dim() != 3 or x.shape[1] != self._cfg.in_channels:
+            raise RuntimeError(f"expected input [B, {self._cfg.in_channels}, T], got {tuple(x.shape)}")
+        return x.detach().contiguous().float()
+
+    def _prep_inference_input(self, c):
+        """(T, in_channels) ndarray or tensor -> (1, in_channels, T) on the model device (hifigan.py:111-113)."""
+        if not isinstance(c, torch.Tensor):
+            c = torch.tensor(c, dtype=torch.float).to(self.device)
+        return c.to(self.device).float().transpose(1, 0).unsqueeze(0)
+
+
+def _fill_hifi(cfg, kind, resblock_kernel_sizes, upsample_rates, upsample_initial_channel, resblock_type,
+               upsample_kernel_sizes, resblock_dilation_sizes, transposedconv, bias, out_channels):
+    if transposedconv is False:
+        raise NotImplementedError("transposedconv=False (UpsampleLayer, modules.py:160-177) is not on the "
+                                  "B200 path yet; every shipped config uses ConvTranspose1d")
+    cfg.kind = kind
+    cfg.in_channels = 80
+    cfg.bias = 1 if bias else 0
+    cfg.num_upsamples = len(upsample_rates)
+    if len(upsample_kernel_sizes) != len(upsample_rates):
+        raise ValueError("upsample_rates and upsample_kernel_sizes differ in length")
+    _set_arr(cfg.upsample_rates, upsample_rates)
+    _set_arr(cfg.upsample_kernel_sizes, upsample_kernel_sizes)
+    _set_arr(cfg.channels, [upsample_initial_channel // (2 ** i) for i in range(len(upsample_rates) + 1)])
+    cfg.pre_kernel_size = 7
+    cfg.post_kernel_size = 7
+    cfg.out_channels = out_channels
+    cfg.num_kernels = len(resblock_kernel_sizes)
+    cfg.resblock_type = 1 if str(resblock_type) == "1" else 2
+    _set_arr(cfg.resblock_kernel_sizes, resblock_kernel_sizes)
+    for j, dils in enumerate(resblock_dilation_sizes[: len(resblock_kernel_sizes)]):
+        cfg.resblock_num_dilations[j] = len(dils)
+        _set_arr(cfg.resblock_dilations[j], dils)
+    cfg.use_final_activation = 1
+    return cfg
+
+
+class HiFiGANGenerator(_NativeGenerator):
+    """Drop-in for model/generator/hifigan.py:13-129."""
+
+    model_name = "hifigan"
+
+    def __init__(self, resblock_kernel_sizes=[3, 7, 11], upsample_rates=[8, 5, 3, 2], upsample_initial_channel=256,
+                 resblock_type="1", upsample_kernel_sizes=[16, 10, 6, 4],
+                 resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], transposedconv=True, bias=True):
+        cfg = _fill_hifi(_lib.FvConfig(), _lib.FV_HIFIGAN, resblock_kernel_sizes, upsample_rates,
+                         upsample_initial_channel, resblock_type, upsample_kernel_sizes, resblock_dilation_sizes,
+                         transposedconv, bias, out_channels=1)
+        super().__init__(cfg)
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_rates)
+
+    def forward(self, x):
+        """[B, 80, T] -> [B, prod(rates) * T]   (hifigan.py:92-108)"""
+        x = self._prep_input(x)
+        B, _, T = x.shape
+        out = torch.empty(B, self.out_length(T), device=x.device, dtype=torch.float32)
+        self._run(x, out, None)
+        return out
+
+    def inference(self, x):
+        """[T, 80] ndarray/tensor -> 1-D waveform   (hifigan.py:110-129)"""
+        return self.forward(self._prep_inference_input(x)).squeeze()
+
+
+class MultiBandHiFiGANGenerator(_NativeGenerator):
+    """Drop-in for model/generator/multiband_hifigan.py:14-137 (4 sub-bands + PQMF synthesis in inference)."""
+
+    model_name = "multiband-hifigan"
+
+    def __init__(self, resblock_kernel_sizes=[3, 7, 11], upsample_rates=[10, 6], upsample_initial_channel=256,
+                 resblock_type="1", upsample_kernel_sizes=[20, 12],
+                 resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]], transposedconv=True, bias=True):
+        cfg = _fill_hifi(_lib.FvConfig(), _lib.FV_MB_HIFIGAN, resblock_kernel_sizes, upsample_rates,
+                         upsample_initial_channel, resblock_type, upsample_kernel_sizes, resblock_dilation_sizes,
+                         transposedconv, bias, out_channels=4)
+        cfg.pqmf_subbands = 4
+        cfg.pqmf_taps = 62
+        super().__init__(cfg)
+        self.pqmf = PQMF()  # 4 band
+        self.num_kernels = len(resblock_kernel_sizes)
+        self.num_upsamples = len(upsample_rates)
+
+    def _extra_state_tensors(self):
+        return {"pqmf.analysis_filter": self.pqmf.analysis_filter, "pqmf.synthesis_filter": self.pqmf.synthesis_filter,
+                "pqmf.updown_filter": self.pqmf.updown_filter}
+
+    def _pqmf_ptrs(self):
+        if self.pqmf.synthesis_filter.device != self.device:
+            self.pqmf.to(self.device)
+        return _lib.ptr(self.pqmf.analysis_filter), _lib.ptr(self.pqmf.synthesis_filter)
+
+    def forward(self, x, synthesize=False):
+        """[B, 80, T] -> sub-bands [B, 4, L]   (multiband_hifigan.py:101-116).
+        ``synthesize=True`` additionally returns the PQMF-synthesised waveform [B, 1, 4L] from the same call."""
+        x = self._prep_input(x)
+        B, _, T = x.shape
+        Lb = self.out_length(T)
+        out = torch.empty(B, 4, Lb, device=x.device, dtype=torch.float32)
+        wav = torch.empty(B, 1, 4 * Lb, device=x.device, dtype=torch.float32) if synthesize else None
+        self._run(x, out, wav)
+        return (out, wav) if synthesize else out
+
+    def inference(self, x):
+        """[T, 80] -> 1-D waveform through PQMF synthesis   (multiband_hifigan.py:118-137)"""
+        _, wav = self.forward(self._prep_inference_input(x), synthesize=True)
+        return wav.squeeze()
+
+
+def _fill_melgan(cfg, kind, in_channels, out_channels, kernel_size, channels, upsample_scales, stack_kernel_size,
+                 stacks, use_final_nonlinear_activation, use_causal_conv, nonlinear_activation,
+                 nonlinear_activation_params, pad):
+    if use_causal_conv:
+        raise NotImplementedError("use_causal_conv=True (modules.py:273-317) is not on the B200 path; "
+                                  "every shipped config sets it False")
+    if nonlinear_activation != "LeakyReLU" or pad != "ReflectionPad1d":
+        raise NotImplementedError("only LeakyReLU + ReflectionPad1d (the shipped configs) are implemented")
+    assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+    if len(channels) != len(upsample_scales) + 1:
+        raise ValueError("channels must have len(upsample_scales) + 1 entries")
+    slope = float(nonlinear_activation_params.get("negative_slope", 0.01))
+    if abs(slope - 0.2) > 1e-12:
+        raise NotImplementedError("negative_slope other than 0.2 is not wired through the C ABI yet")
+    cfg.kind = kind
+    cfg.in_channels = in_channels
+    cfg.bias = 1
+    cfg.num_upsamples = len(upsample_scales)
+    _set_arr(cfg.upsample_rates, upsample_scales)
+    _set_arr(cfg.upsample_kernel_sizes, [2 * s for s in upsample_scales])   # melgan.py:81
+    _set_arr(cfg.channels, channels)
+    cfg.pre_kernel_size = kernel_size
+    cfg.post_kernel_size = kernel_size
+    cfg.out_channels = out_channels
+    cfg.stacks = stacks
+    cfg.stack_kernel_size = stack_kernel_size
+    cfg.use_final_activation = 1 if use_final_nonlinear_activation else 0
+    return cfg
+
+
+class MelGANGenerator(_NativeGenerator):
+    """Drop-in for model/generator/melgan.py:17-185."""
+
+    model_name = "melgan"
+
+    def __init__(self, in_channels=80, out_channels=1, kernel_size=7, channels=[512, 256, 128, 64, 32], bias=True,
+                 upsample_scales=[10, 6, 2, 2], stack_kernel_size=3, stacks=3, nonlinear_activation="LeakyReLU",
+                 nonlinear_activation_params={"negative_slope": 0.2}, pad="ReflectionPad1d", pad_params={},
+                 use_final_nonlinear_activation=True, use_weight_norm=True, use_causal_conv=False):
+        if not bias:
+            raise NotImplementedError("bias=False MelGAN is not wired (no shipped config uses it)")
+        cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_MELGAN, in_channels, out_channels, kernel_size, channels,
+                           upsample_scales, stack_kernel_size, stacks, use_final_nonlinear_activation,
+                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad)
+        super().__init__(cfg, use_weight_norm=use_weight_norm)
+        self.pqmf = None
+
+    def forward(self, c):
+        """[B, 80, T] -> [B, prod(scales) * T]   (melgan.py:125-136; channel 0 of the 1-channel output)"""
+        c = self._prep_input(c)
+        B, _, T = c.shape
+        Lo = self.out_length(T)
+        oc = self._cfg.out_channels
+        out = torch.empty(B, oc, Lo, device=c.device, dtype=torch.float32)
+        self._run(c, out, None)
+        return out[:, 0, :]
+
+    def inference(self, c):
+        """[T, 80] -> waveform   (melgan.py:172-185)"""
+        c = self._prep_input(self._prep_inference_input(c))
+        Lo = self.out_length(c.shape[2])
+        out = torch.empty(1, self._cfg.out_channels, Lo, device=c.device, dtype=torch.float32)
+        self._run(c, out, None)
+        return out.squeeze()
+
+
+class BasisMelGANGenerator(_NativeGenerator):
+    """Drop-in for model/generator/basis_melgan.py:19-212."""
+
+    model_name = "basis-melgan"
+
+    def __init__(self, basis_signal_weight, L=30, in_channels=80, out_channels=256, kernel_size=7,
+                 channels=[256, 256, 256], bias=True, upsample_scales=[4, 4], stack_kernel_size=3, stacks=3,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.2},
+                 pad="ReflectionPad1d", pad_params={}, use_final_nonlinear_activation=True, use_weight_norm=True,
+                 use_causal_conv=False, transposedconv=True, lastlinear=False):
+        if not bias:
+            raise NotImplementedError("bias=False Basis-MelGAN is not wired (no shipped config uses it)")
+        if transposedconv is False or lastlinear:
+            raise NotImplementedError("transposedconv=False / lastlinear=True are not on the B200 path "
+                                      "(no shipped config uses them)")
+        cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_BASIS_MELGAN, in_channels, channels[-1], kernel_size, channels,
+                           upsample_scales, stack_kernel_size, stacks, use_final_nonlinear_activation,
+                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad)
+        cfg.basis_L = L
+        bw = torch.as_tensor(basis_signal_weight).float()
+        if tuple(bw.shape) != (L, channels[-1]):
+            raise ValueError(f"basis_signal_weight must be [L={L}, {channels[-1]}], got {tuple(bw.shape)}")
+        super().__init__(cfg, use_weight_norm=use_weight_norm)
+        with torch.no_grad():
+            self._view("basis_signal.layer.weight").copy_(bw)   # nn.Linear weight, no weight norm (modules.py:260-261)
+        self.L = L
+        self.pqmf = None
+
+    def forward(self, c, return_weight=True):
+        """[B, 80, T] -> (est_source - zero_est [B, 16T*15], weight - zero_weight [B, 16T, C])
+        (basis_melgan.py:140-162).  The input-independent zero pass rides along as one extra utterance."""
+        c = self._prep_input(c)
+        B, _, T = c.shape
+        n = self.out_length(T)
+        hop = self.L // 2
+        est = torch.empty(B, n, device=c.device, dtype=torch.float32)
+        weight = torch.empty(B, n // hop, self._cfg.out_channels, device=c.device,
+                             dtype=torch.float32) if return_weight else None
+        self._run(c, est, weight)
+        return est, weight
+
+    def inference(self, c):
+        """[T, 80] -> untruncated (16T+1)*15 samples, no bias subtraction   (basis_melgan.py:196-208)"""
+        c = self._prep_input(self._prep_inference_input(c))
+        n = self.out_length(c.shape[2], _lib.FV_FWD_BASIS_INFERENCE)
+        out = torch.empty(1, n, device=c.device, dtype=torch.float32)
+        self._run(c, out, None, flags=_lib.FV_FWD_BASIS_INFERENCE)
+        return out.squeeze()
+
+    def test(self, weight):
+        """basis_signal(weight): Linear + overlap-add on a given weight tensor (basis_melgan.py:210-212)."""
+        raise NotImplementedError("use forward()/inference(); the standalone basis layer is exposed as "
+                                  "fv_overlap_add in the C ABI")
+
+
+def build_generator(model_name: str, config: dict):
+    """Construct a generator from a reference YAML dict exactly as bin/synthesize.py:25-68 does."""
+    if model_name == "melgan":
+        return MelGANGenerator(in_channels=config["in_channels"], out_channels=config["out_channels"],
+                               kernel_size=config["kernel_size"], channels=config["channels"],
+                               upsample_scales=config["upsample_scales"],
+                               stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
+                               use_weight_norm=config["use_weight_norm"], use_causal_conv=config["use_causal_conv"])
+    if model_name == "hifigan":
+        cls = HiFiGANGenerator
+    elif model_name == "multiband-hifigan":
+        cls = MultiBandHiFiGANGenerator
+    elif model_name == "basis-melgan":
+        basis_signal_weight = torch.zeros(config["L"], config["out_channels"]).float()
+        return BasisMelGANGenerator(basis_signal_weight=basis_signal_weight, L=config["L"],
+                                    in_channels=config["in_channels"], out_channels=config["out_channels"],
+                                    kernel_size=config["kernel_size"], channels=config["channels"],
+                                    upsample_scales=config["upsample_scales"],
+                                    stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
+                                    use_weight_norm=config["use_weight_norm"],
+                                    use_causal_conv=config["use_causal_conv"],
+                                    transposedconv=config["transposedconv"])
+    else:
+        raise Exception("no model find!")
+    return cls(resblock_kernel_sizes=config["resblock_kernel_sizes"], upsample_rates=config["upsample_rates"],
+               upsample_initial_channel=config["upsample_initial_channel"], resblock_type=config["resblock_type"],
+               upsample_kernel_sizes=config["upsample_kernel_sizes"],
+               resblock_dilation_sizes=config["resblock_dilation_sizes"], transposedconv=config["transposedconv"],
+               bias=config["bias"])

@@ -1,0 +1,146 @@
+"""Host-side logic (no GPU): C-ABI surface, parameter tables, weight-norm folding, config errors."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, MODEL_KEYS, REPO, folded_weights
+from fastvocoder_b200 import _lib, build_generator
+from fastvocoder_b200.pqmf import PQMF, design_filters
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, "include", "fastvocoder_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(fv_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} not exported by {_lib.LIB_PATH}"
+    assert _lib.lib().fv_abi_version() == _lib.FV_ABI_VERSION
+
+
+@pytest.mark.parametrize("key", MODEL_KEYS)
+def test_state_dict_keys_match_reference(specs, key):
+    m = build_generator(specs[key]["model_name"], specs[key]["config"])
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {k: tuple(s) for k, s in specs[key]["spec_wn"]}           # checkpoint (weight-norm) form
+    m.eval()
+    m.remove_weight_norm()
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {k: tuple(s) for k, s in specs[key]["spec_folded"]}       # after remove_weight_norm()
+
+
+@pytest.mark.parametrize("key,name", [("hifigan-light", "hifigan"), ("melgan-original", "melgan")])
+def test_weight_norm_fold_bit_exact(specs, key, name):
+    g = dict(np.load(os.path.join(GOLDEN, f"fold_{key}.npz")))
+    m = build_generator(name, specs[key]["config"])
+    sd = m.state_dict()
+    layers = sorted({k[:-len(".weight_g")] for k in g if k.endswith(".weight_g")})
+    for p in layers:
+        sd[p + ".weight_g"] = torch.from_numpy(g[p + ".weight_g"])
+        sd[p + ".weight_v"] = torch.from_numpy(g[p + ".weight_v"])
+    m.load_state_dict(sd)
+    m.remove_weight_norm()
+    out = m.state_dict()
+    for p in layers:
+        assert np.array_equal(out[p + ".weight"].numpy(), g[p + ".weight"]), p   # torch's own fold -> same bits
+
+
+def test_state_dict_round_trip_both_forms(specs):
+    key = "basis-melgan-light"
+    m = build_generator("basis-melgan", specs[key]["config"])
+    sd_wn = m.state_dict()
+    m2 = build_generator("basis-melgan", specs[key]["config"])
+    m2.load_state_dict(sd_wn)
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd_wn[k]), k
+    m.remove_weight_norm()
+    m2.remove_weight_norm()
+    a, b = m.state_dict(), m2.state_dict()
+    assert a.keys() == b.keys()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # folded dict loads too, and strictness is enforced
+    m3 = build_generator("basis-melgan", specs[key]["config"])
+    m3.load_state_dict(a)
+    with pytest.raises(RuntimeError):
+        bad = dict(a)
+        bad.pop("melgan.1.weight")
+        m3.load_state_dict(bad)
+    with pytest.raises(RuntimeError):
+        bad = dict(a)
+        bad["melgan.1.weight"] = torch.zeros(3, 3, 3)
+        m3.load_state_dict(bad)
+
+
+def test_synthetic_weights_load(specs):
+    key = "multiband-hifigan-light"
+    m = build_generator("multiband-hifigan", specs[key]["config"])
+    w = folded_weights(specs, key)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    sd = m.state_dict()
+    for k, v in w.items():
+        assert np.array_equal(sd[k].numpy(), v)
+    assert "pqmf.synthesis_filter" in sd and "weight_g" not in "".join(sd.keys())
+
+
+def test_error_conventions(specs):
+    with pytest.raises(Exception, match="no model find!"):
+        build_generator("wavernn", {})
+    cfg = dict(specs["melgan-original"]["config"])
+    cfg["kernel_size"] = 6
+    with pytest.raises(AssertionError, match="Not support even number kernel size."):
+        build_generator("melgan", cfg)
+    m = build_generator("hifigan", specs["hifigan-light"]["config"])
+    with pytest.raises(_lib.FvError, match="no CPU"):
+        m(torch.zeros(1, 80, 8))                      # no CPU fallback: must fail loudly
+    bad = _lib.FvConfig()
+    bad.kind = 17
+    h = C.c_void_p()
+    assert _lib.lib().fv_create(C.byref(bad), C.byref(h)) == -1
+    assert b"no model find" in _lib.lib().fv_last_error()
+
+
+def test_output_lengths(specs):
+    want = specs["_demo_lengths_T585"]
+    m = build_generator("hifigan", specs["hifigan-light"]["config"])
+    assert m.out_length(585) == want["hifigan-light"]
+    m = build_generator("multiband-hifigan", specs["multiband-hifigan-light"]["config"])
+    assert 4 * m.out_length(585) == want["multiband-hifigan-light"]
+    m = build_generator("multiband-hifigan", specs["multiband-hifigan-large"]["config"])
+    assert 4 * m.out_length(585) == want["multiband-hifigan-large"]            # the 60T-20 quirk
+    m = build_generator("basis-melgan", specs["basis-melgan-light"]["config"])
+    assert m.out_length(585, _lib.FV_FWD_BASIS_INFERENCE) == want["basis-melgan-light"]
+    assert m.out_length(585) == 240 * 585
+    m = build_generator("melgan", specs["melgan-original"]["config"])
+    assert m.out_length(200) == 48000
+
+
+def test_flops_accounting_matches_survey(specs):
+    # MAC per mel frame
+    for key, name, macs in [("hifigan-light", "hifigan", 62.47e6), ("multiband-hifigan-light", "multiband-hifigan", 53.50e6),
+                            ("melgan-original", "melgan", 45.48e6), ("hifigan-large", "hifigan", 249.5e6)]:
+        m = build_generator(name, specs[key]["config"])
+        per_frame = m.forward_flops(1, 1000) / 2 / 1000
+        assert abs(per_frame - macs) / macs < 2e-3, (key, per_frame)
+    m = build_generator("basis-melgan", specs["basis-melgan-light"]["config"])
+    one_pass = m.forward_flops(1, 1000, _lib.FV_FWD_BASIS_INFERENCE) / 2 / 1000
+    # SURVEY lists 22.44 M with the basis Linear as 0.014 M; it is 256*30*16 = 0.123 M/frame -> 22.55 M
+    assert abs(one_pass - 22.548e6) / 22.548e6 < 1e-3
+
+
+def test_pqmf_design_is_byte_identical(specs, ops_golden):
+    ana, syn = design_filters()
+    assert hashlib.sha256(ana.numpy().tobytes()).hexdigest() == specs["_pqmf"]["analysis_sha256"]
+    assert hashlib.sha256(syn.numpy().tobytes()).hexdigest() == specs["_pqmf"]["synthesis_sha256"]
+    p = PQMF()
+    assert set(p.state_dict()) == {"analysis_filter", "synthesis_filter", "updown_filter"}
+    assert np.array_equal(p.synthesis_filter.numpy(), ops_golden["pqmf_synthesis_filter"])
+    with pytest.raises(_lib.FvError):
+        p.synthesis(torch.zeros(1, 4, 8))             # CPU tensor: no fallback
