@@ -60,6 +60,7 @@ SIGNATURES = {
     "fv_last_error": (C.c_char_p, []),
     "fv_abi_version": (_I, []),
     "fv_launch_count": (C.c_int64, []),
+    "fv_tc_launch_count": (C.c_int64, []),
     "fv_create": (_I, [C.POINTER(FvConfig), C.POINTER(_P)]),
     "fv_destroy": (None, [_P]),
     "fv_num_params": (_I, [_P]),

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -16,6 +17,7 @@
 
 namespace fv {
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_tc_launches{0};
 thread_local std::string g_err;
 
 static int fail(int code, const char* fmt, ...) {
@@ -124,7 +126,8 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   if (c.Lin <= 0 || c.B <= 0) return fail(FV_EINVAL, "empty batch or sequence");
   if (c.pad_mode == PAD_REFLECT && a.pad_left >= c.Lin)
     return fail(FV_EINVAL, "ReflectionPad1d needs pad (%d) < length (%lld)", a.pad_left, c.Lin);
-  if (c.allow_tc && tcl && tcl->eligible) {
+  static const bool tc_disabled = getenv("FV_DISABLE_TC") != nullptr;  // operational kill switch
+  if (c.allow_tc && !tc_disabled && tcl && tcl->eligible) {
     int rc = launch_conv_tc(a, *tcl, st);
     if (rc == 0) return FV_OK;
     if (rc < 0) return fail(FV_ECUDA, "tcgen05 conv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -356,6 +359,7 @@ extern "C" {
 const char* fv_last_error(void) { return g_err.c_str(); }
 int fv_abi_version(void) { return FV_ABI_VERSION; }
 int64_t fv_launch_count(void) { return (int64_t)g_launches.load(); }
+int64_t fv_tc_launch_count(void) { return (int64_t)g_tc_launches.load(); }
 
 int fv_create(const fv_config* cfg, fv_handle** out) {
   if (!cfg || !out) return fail(FV_EINVAL, "null argument");

@@ -92,6 +92,8 @@ const char* fv_last_error(void);
 int fv_abi_version(void);
 /* number of kernels this library launched on this process since load (bench `gpu_launches`) */
 int64_t fv_launch_count(void);
+/* how many of those were tcgen05 (tensor-core) convolution launches */
+int64_t fv_tc_launch_count(void);
 
 /* ---- model life cycle (host only until fv_bind_weights) ----------------------------------------
  * fv_create      <- Generator.__init__(**yaml)            hifigan.py:14 melgan.py:20 basis_melgan.py:22

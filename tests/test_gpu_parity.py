@@ -4,6 +4,7 @@ Tolerances (fp32 path, stated per north_star): waveform max-abs <= 1e-4 against 
 PQMF / overlap-add index arithmetic bit-exact.  Nothing here reads /root/reference.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -18,6 +19,7 @@ from oracle import torch_port as P
 pytestmark = pytest.mark.gpu
 TOL = 1e-4          # north_star: within 1e-4 max-abs of the reference
 TIGHT = 2e-5        # what the exact-fp32 and split-fp16 paths actually achieve on these fixtures
+TC_DISABLED = bool(os.environ.get("FV_DISABLE_TC"))   # library-wide kill switch of the tcgen05 path
 
 
 def dev(a):
@@ -72,10 +74,14 @@ def test_conv1d(Cin, Cout, K, d, L, pad_mode, slope, tanh, use_tc):
     if tanh:
         want = np.tanh(want)
     y = torch.empty(B, Cout, L, device="cuda")
-    _lib.check(_lib.lib().fv_conv1d(_lib.ptr(dev(x)), _lib.ptr(dev(w)), _lib.ptr(dev(b)), _lib.ptr(dev(r)),
+    dx, dw, db, dr = dev(x), dev(w), dev(b), dev(r)            # keep alive across the call
+    tc0 = _lib.lib().fv_tc_launch_count()
+    _lib.check(_lib.lib().fv_conv1d(_lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dr),
                                     _lib.ptr(y), B, Cin, Cout, L, K, d, pad_mode, slope, tanh, use_tc, stream()))
     err = np.abs(y.cpu().numpy() - want).max()
     assert err < 2e-5, err
+    if use_tc and Cin % 16 == 0 and Cout % 16 == 0 and not TC_DISABLED:
+        assert _lib.lib().fv_tc_launch_count() > tc0, "eligible shape did not run on the tcgen05 path"
 
 
 @pytest.mark.parametrize("use_tc", [0, 1])
@@ -87,7 +93,8 @@ def test_conv_transpose1d_golden(ops_golden, k, s, use_tc):
     B, Cin, Lin = x.shape
     Cout = w.shape[1]
     y = torch.full(want.shape, float("nan"), device="cuda", dtype=torch.float32)
-    _lib.check(_lib.lib().fv_conv_transpose1d(_lib.ptr(dev(x)), _lib.ptr(dev(w)), _lib.ptr(dev(b)), _lib.ptr(y), B,
+    dx, dw, db = dev(x), dev(w), dev(b)
+    _lib.check(_lib.lib().fv_conv_transpose1d(_lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(y), B,
                                               Cin, Cout, Lin, k, s, s // 2 + s % 2, s % 2, -1.0, use_tc, stream()))
     got = y.cpu().numpy()
     assert not np.isnan(got).any(), "some output samples were never written"
@@ -104,8 +111,12 @@ def test_conv_transpose1d_wide_with_lrelu(use_tc):
     want = O.conv_transpose1d(O.leaky_relu(x.astype(np.float64), 0.1), w.astype(np.float64), b.astype(np.float64),
                               stride=s, padding=3, output_padding=1)
     y = torch.empty(want.shape, device="cuda", dtype=torch.float32)
-    _lib.check(_lib.lib().fv_conv_transpose1d(_lib.ptr(dev(x)), _lib.ptr(dev(w)), _lib.ptr(dev(b)), _lib.ptr(y), B,
+    dx, dw, db = dev(x), dev(w), dev(b)
+    tc0 = _lib.lib().fv_tc_launch_count()
+    _lib.check(_lib.lib().fv_conv_transpose1d(_lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(y), B,
                                               Cin, Cout, Lin, k, s, 3, 1, 0.1, use_tc, stream()))
+    if use_tc and not TC_DISABLED:
+        assert _lib.lib().fv_tc_launch_count() > tc0
     assert np.abs(y.cpu().numpy() - want).max() < 2e-5
 
 
@@ -130,7 +141,8 @@ def test_resblock1_golden(ops_golden, k, use_tc):
     dil = (C.c_int * 3)(1, 3, 5)
     y = torch.empty(B, Cc, L, device="cuda")
     scratch = torch.empty(2 * B * Cc * L, device="cuda")
-    _lib.check(_lib.lib().fv_resblock1(_lib.ptr(dev(x)), _ptr_array(w1), _ptr_array(b1), _ptr_array(w2),
+    dx = dev(x)
+    _lib.check(_lib.lib().fv_resblock1(_lib.ptr(dx), _ptr_array(w1), _ptr_array(b1), _ptr_array(w2),
                                        _ptr_array(b2), dil, 3, _lib.ptr(y), _lib.ptr(scratch), B, Cc, L, k, use_tc,
                                        stream()))
     assert np.abs(y.cpu().numpy() - want).max() < 1e-5
@@ -142,11 +154,14 @@ def test_residual_stack_golden(ops_golden, d, use_tc):
     x = ops_golden[f"resstack_d{d}_x"]
     want = ops_golden[f"resstack_d{d}_y64"]
     B, Cc, L = x.shape
-    g = lambda n: dev(ops_golden[f"resstack_d{d}_p_{n}"])  # noqa: E731
+    t = {n: dev(ops_golden[f"resstack_d{d}_p_{n}"]) for n in ("stack.2.weight", "stack.2.bias", "stack.4.weight",
+                                                              "stack.4.bias", "skip_layer.weight", "skip_layer.bias")}
+    g = t.__getitem__
     y = torch.empty(B, Cc, L, device="cuda")
     scratch = torch.empty(2 * B * Cc * L, device="cuda")
+    dx = dev(x)
     _lib.check(_lib.lib().fv_residual_stack(
-        _lib.ptr(dev(x)), _lib.ptr(g("stack.2.weight")), _lib.ptr(g("stack.2.bias")), _lib.ptr(g("stack.4.weight")),
+        _lib.ptr(dx), _lib.ptr(g("stack.2.weight")), _lib.ptr(g("stack.2.bias")), _lib.ptr(g("stack.4.weight")),
         _lib.ptr(g("stack.4.bias")), _lib.ptr(g("skip_layer.weight")), _lib.ptr(g("skip_layer.bias")), _lib.ptr(y),
         _lib.ptr(scratch), B, Cc, L, 3, d, use_tc, stream()))
     assert np.abs(y.cpu().numpy() - want).max() < 1e-5
@@ -156,9 +171,10 @@ def test_overlap_add_bit_exact(ops_golden):
     sig = ops_golden["ola_signal"]                     # [3, 17, 30]
     want = ops_golden["ola_out_step15"]
     out = torch.empty(want.shape, device="cuda")
-    _lib.check(_lib.lib().fv_overlap_add(_lib.ptr(dev(sig)), 3, 17, 30, 15, _lib.ptr(out), stream()))
+    dsig = dev(sig)
+    _lib.check(_lib.lib().fv_overlap_add(_lib.ptr(dsig), 3, 17, 30, 15, _lib.ptr(out), stream()))
     assert np.array_equal(out.cpu().numpy(), want)
-    assert _lib.lib().fv_overlap_add(_lib.ptr(dev(sig)), 3, 17, 30, 10, _lib.ptr(out), stream()) == -1
+    assert _lib.lib().fv_overlap_add(_lib.ptr(dsig), 3, 17, 30, 10, _lib.ptr(out), stream()) == -1
 
 
 def test_pqmf_bit_exact_on_impulses_and_close_on_noise(ops_golden):
@@ -330,3 +346,82 @@ def test_synthesizer_api(tmp_path, specs):
     want = O.encode_16bits(g["realmel_inference_f32"].copy(), 0.4)
     assert np.abs(pcm.astype(np.int32) - want.astype(np.int32)).max() <= 2
     assert os.path.exists(str(wav_path)[:-3] + "remove.wav") and os.path.exists(str(wav_path)[:-3] + "bias.wav")
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 path
+@pytest.mark.parametrize("Cin,Cout,K,d,L,pad_mode,slope", [
+    (16, 16, 3, 1, 128, 0, 0.1),          # exactly one M tile
+    (16, 16, 7, 5, 129, 0, 0.1),          # one position into the second tile
+    (128, 128, 11, 5, 700, 0, 0.1),       # widest HiFi-light layer: multi M-tile CTA, 88 K-blocks through the ring
+    (64, 64, 11, 3, 2000, 0, 0.1),
+    (32, 32, 3, 5, 5000, 0, 0.1),
+    (256, 256, 3, 9, 300, 1, 0.2),        # Basis-MelGAN ResidualStack (reflect, d=9), N tile 256
+    (256, 256, 1, 1, 200, 0, 0.2),        # 1x1
+    (80, 512, 7, 1, 90, 1, -1.0),         # MelGAN first conv: N tiled 2 x 256
+    (80, 256, 7, 1, 1000, 0, -1.0),       # HiFi conv_pre at T=1000
+    (512, 512, 3, 1, 64, 0, 0.1),         # big-channel case (HiFi large stage 0 is 256; stress K loop)
+])
+def test_tc_conv_shapes(Cin, Cout, K, d, L, pad_mode, slope):
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    rng = np.random.default_rng(Cin + 7 * Cout + K + d + L)
+    B = 2
+    x = (rng.standard_normal((B, Cin, L)) * 1.5).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, K)) / np.sqrt(Cin * K)).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    r = rng.standard_normal((B, Cout, L)).astype(np.float32)
+    xt = torch.from_numpy(x).double()
+    if slope >= 0:
+        xt = torch.nn.functional.leaky_relu(xt, slope)
+    p = (K - 1) * d // 2
+    xt = torch.nn.functional.pad(xt, (p, p), mode="reflect" if pad_mode else "constant")
+    want = (torch.nn.functional.conv1d(xt, torch.from_numpy(w).double(), torch.from_numpy(b).double(), dilation=d)
+            + torch.from_numpy(r).double()).numpy()
+    y = torch.empty(B, Cout, L, device="cuda")
+    dx, dw, db, dr = dev(x), dev(w), dev(b), dev(r)
+    tc0 = _lib.lib().fv_tc_launch_count()
+    _lib.check(_lib.lib().fv_conv1d(_lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(dr), _lib.ptr(y), B, Cin, Cout,
+                                    L, K, d, pad_mode, slope, 0, 1, stream()))
+    assert _lib.lib().fv_tc_launch_count() > tc0, "did not run on the tcgen05 path"
+    err = np.abs(y.cpu().numpy() - want).max()
+    assert err < 2e-5, err            # split-fp16 3-pass: fp32-level accuracy
+
+
+@pytest.mark.parametrize("Cin,Cout,k,s,Lin", [(256, 128, 16, 8, 100), (128, 64, 10, 5, 333), (32, 16, 4, 2, 4000),
+                                              (256, 256, 8, 4, 64), (64, 32, 16, 10, 50)])
+def test_tc_conv_transpose_shapes(Cin, Cout, k, s, Lin):
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    rng = np.random.default_rng(Cin + Cout + k + s)
+    B = 2
+    x = rng.standard_normal((B, Cin, Lin)).astype(np.float32)
+    w = (rng.standard_normal((Cin, Cout, k)) / np.sqrt(2 * Cin)).astype(np.float32)
+    b = (rng.standard_normal(Cout) * 0.1).astype(np.float32)
+    p, op = s // 2 + s % 2, s % 2
+    want = torch.nn.functional.conv_transpose1d(torch.nn.functional.leaky_relu(torch.from_numpy(x).double(), 0.1),
+                                                torch.from_numpy(w).double(), torch.from_numpy(b).double(), stride=s,
+                                                padding=p, output_padding=op).numpy()
+    y = torch.full(want.shape, float("nan"), device="cuda", dtype=torch.float32)
+    dx, dw, db = dev(x), dev(w), dev(b)
+    tc0 = _lib.lib().fv_tc_launch_count()
+    _lib.check(_lib.lib().fv_conv_transpose1d(_lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(y), B, Cin, Cout, Lin,
+                                              k, s, p, op, 0.1, 1, stream()))
+    assert _lib.lib().fv_tc_launch_count() > tc0
+    got = y.cpu().numpy()
+    assert not np.isnan(got).any()
+    assert np.abs(got - want).max() < 2e-5
+
+
+def test_model_uses_tensor_cores_when_enabled(specs):
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    m = make_model(specs, "hifigan-light", tc=True)
+    mel = dev(synth_mel(1, 16, seed=2))
+    t0 = _lib.lib().fv_tc_launch_count()
+    m(mel)
+    used = _lib.lib().fv_tc_launch_count() - t0
+    assert used >= 70, used            # 72 ResBlock convs + conv_pre + 4 upsamplers are eligible
+    m.use_tensor_cores = False
+    t0 = _lib.lib().fv_tc_launch_count()
+    m(mel)
+    assert _lib.lib().fv_tc_launch_count() == t0
