@@ -51,6 +51,12 @@ class FvConfig(C.Structure):
     ]
 
 
+class FvProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("kernel", C.c_int32), ("Cin", C.c_int32), ("N", C.c_int32),
+                ("K", C.c_int32), ("dil", C.c_int32), ("positions", C.c_int64), ("flops", C.c_double),
+                ("bytes", C.c_double), ("ms", C.c_float), ("reserved", C.c_float)]
+
+
 # name -> (restype, argtypes); exactly the symbols include/fastvocoder_b200.h declares
 _P = C.c_void_p
 _PP = C.POINTER(C.c_void_p)
@@ -71,6 +77,8 @@ SIGNATURES = {
     "fv_workspace_bytes": (_I, [_P, _I, _I, C.POINTER(C.c_size_t)]),
     "fv_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, C.c_size_t, _I, _P]),
     "fv_forward_flops": (_I, [_P, _I, _I, _I, C.POINTER(C.c_double)]),
+    "fv_forward_profile": (_I, [_P, _P, _I, _I, _P, _P, _P, C.c_size_t, _I, _P, C.POINTER(FvProfileEntry), _I,
+                                C.POINTER(_I)]),
     "fv_conv1d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P]),
     "fv_conv_transpose1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "fv_resblock1": (_I, [_P, _PP, _PP, _PP, _PP, C.POINTER(_I), _I, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -92,7 +92,8 @@ static long long layer_out_len(const Layer& l, long long Lin) {
 }
 
 static int run_layer(const Layer& l, const float* wd, const float* bias, const TcLayer* tcl, const LayerCall& c,
-                     cudaStream_t st) {
+                     cudaStream_t st, int* used_tc = nullptr) {
+  if (used_tc) *used_tc = 0;
   ConvArgs a{};
   a.x = c.x; a.w = wd; a.bias = bias; a.res = c.res; a.y = c.y;
   a.B = c.B; a.Cin = l.Cin; a.N = l.N; a.Lin = (int)c.Lin; a.K = l.Kd; a.dil = l.dil;
@@ -129,7 +130,10 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   static const bool tc_disabled = getenv("FV_DISABLE_TC") != nullptr;  // operational kill switch
   if (c.allow_tc && !tc_disabled && tcl && tcl->eligible) {
     int rc = launch_conv_tc(a, *tcl, st);
-    if (rc == 0) return FV_OK;
+    if (rc == 0) {
+      if (used_tc) *used_tc = 1;
+      return FV_OK;
+    }
     if (rc < 0) return fail(FV_ECUDA, "tcgen05 conv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     // rc > 0: shape not handled by the tensor-core kernel -> exact fp32 kernel (same GPU, not a CPU fallback)
   }
@@ -160,8 +164,18 @@ static int eff_batch(const Model& m, int B, int flags) {
   return (m.cfg.kind == FV_BASIS_MELGAN && !(flags & FV_FWD_BASIS_INFERENCE)) ? B + 1 : B;
 }
 
+struct Profiler {
+  struct Rec {
+    int layer, used_tc;
+    long long Lin;
+    int B;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Rec> recs;
+};
+
 static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* ws,
-                        size_t ws_bytes, int flags, cudaStream_t st) {
+                        size_t ws_bytes, int flags, cudaStream_t st, Profiler* prof = nullptr) {
   const Model& m = h->model;
   const fv_config& c = m.cfg;
   const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES);
@@ -183,9 +197,18 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     return m.layers[li].b_param >= 0 ? h->packed + m.params[m.layers[li].b_param].offset : nullptr;
   };
   auto tcl = [&](int li) -> const TcLayer* { return h->tc.layer(li); };
-  auto call = [&](int li, LayerCall lc) {
+  auto call = [&](int li, LayerCall lc) -> int {
     lc.allow_tc = tc_ok;
-    return run_layer(m.layers[li], wd(li), bias(li), tcl(li), lc, st);
+    if (!prof) return run_layer(m.layers[li], wd(li), bias(li), tcl(li), lc, st);
+    Profiler::Rec r{};
+    r.layer = li; r.Lin = lc.Lin; r.B = lc.B;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess)
+      return fail(FV_ECUDA, "cudaEventCreate failed");
+    cudaEventRecord(r.e0, st);
+    int rc = run_layer(m.layers[li], wd(li), bias(li), tcl(li), lc, st, &r.used_tc);
+    cudaEventRecord(r.e1, st);
+    prof->recs.push_back(r);
+    return rc;
   };
 
   const float* x_in = mel;
@@ -445,6 +468,41 @@ int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* 
     return fail(FV_EINVAL, "ReflectionPad1d needs T > %d", (h->model.cfg.pre_kernel_size - 1) / 2);
   if (h->model.out_length(T, flags) <= 0) return fail(FV_EINVAL, "T too small for this architecture");
   return forward_impl(h, mel, B, T, out, out2, workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int fv_forward_profile(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,
+                       size_t workspace_bytes, int flags, void* stream, fv_profile_entry* entries, int cap,
+                       int* count) {
+  if (!h || !mel || !out || !workspace || !entries || !count) return fail(FV_EINVAL, "null argument");
+  if (!h->bound) return fail(FV_ESTATE, "fv_forward_profile before fv_bind_weights");
+  Profiler prof;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = forward_impl(h, mel, B, T, out, out2, workspace, workspace_bytes, flags, st, &prof);
+  cudaError_t e = cudaStreamSynchronize(st);
+  int n = 0;
+  for (auto& r : prof.recs) {
+    if (rc == 0 && e == cudaSuccess && n < cap) {
+      const Layer& l = h->model.layers[r.layer];
+      fv_profile_entry& o = entries[n++];
+      memset(&o, 0, sizeof o);
+      strncpy(o.name, h->model.params[l.w_param].name.c_str(), sizeof(o.name) - 1);
+      o.kernel = r.used_tc;
+      o.Cin = l.Cin; o.N = l.N; o.K = l.Kd; o.dil = l.dil;
+      o.positions = (int64_t)r.B * r.Lin;
+      // algorithmic MACs: every input sample meets every (Cout, tap) of the reference op
+      o.flops = 2.0 * (double)l.Cin * l.Cout * l.K * (double)r.Lin * r.B;
+      // algorithmic HBM bytes if nothing were cached: read x, write y (+ read residual for half the convs, ignored)
+      o.bytes = 4.0 * r.B * ((double)l.Cin * r.Lin + (double)l.Cout * (double)layer_out_len(l, r.Lin) /
+                                                         (l.type == L_BASIS ? l.Cout : 1));
+      cudaEventElapsedTime(&o.ms, r.e0, r.e1);
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  *count = n;
+  if (rc) return rc;
+  FV_CUDA(e);
+  return FV_OK;
 }
 
 int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops) {

@@ -219,6 +219,26 @@ class _NativeGenerator(torch.nn.Module):
                                              _lib.ptr(ws), ws.numel(), flags, _lib.current_stream_ptr()),
                        "fv_forward")
 
+    def profile_forward(self, x, flags: int = 0):
+        """One forward with per-layer CUDA-event timing (fv_forward_profile). Returns a list of dicts."""
+        x = self._prep_input(x)
+        B, _, T = x.shape
+        ws = self._get_workspace(B, T)
+        out = torch.empty(B * max(1, self._cfg.out_channels if self._cfg.kind != _lib.FV_BASIS_MELGAN else 1)
+                          * self.out_length(T, flags), device=x.device, dtype=torch.float32)
+        if not self.use_tensor_cores:
+            flags |= _lib.FV_FWD_NO_TENSOR_CORES
+        cap = 1024
+        entries = (_lib.FvProfileEntry * cap)()
+        n = C.c_int()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fv_forward_profile(self._handle, _lib.ptr(x), B, T, _lib.ptr(out), None,
+                                                     _lib.ptr(ws), ws.numel(), flags, _lib.current_stream_ptr(),
+                                                     entries, cap, C.byref(n)), "fv_forward_profile")
+        return [dict(name=e.name.decode(), kernel="tcgen05" if e.kernel else "ffma", Cin=e.Cin, N=e.N, K=e.K,
+                     dil=e.dil, positions=e.positions, flops=e.flops, bytes=e.bytes, ms=e.ms)
+                for e in entries[: n.value]]
+
     def _prep_input(self, x):
         if not isinstance(x, torch.Tensor):
             raise TypeError("forward expects a torch.Tensor [B, in_channels, T]")

@@ -129,6 +129,22 @@ int fv_out_length(const fv_handle* h, int T, int flags, int64_t* out_len);
 int fv_workspace_bytes(const fv_handle* h, int B, int T, size_t* bytes);
 int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,
                size_t workspace_bytes, int flags, void* stream);
+/* Same as fv_forward, but brackets every learned layer with CUDA events on `stream` and reports, per layer
+ * launch: which kernel ran (0 = fp32 CUDA-core conv, 1 = tcgen05 conv), its algorithmic FLOPs / bytes and its
+ * device time.  Synchronises the stream.  bench.py uses it for the live roofline numbers. */
+typedef struct fv_profile_entry {
+  char name[64];       /* parameter name of the layer's weight, e.g. "resblocks.2.convs1.1.weight" */
+  int32_t kernel;      /* 0 fp32 FFMA conv, 1 tcgen05 split-fp16 conv */
+  int32_t Cin, N, K, dil;
+  int64_t positions;   /* B * input length */
+  double flops;        /* 2 * MAC of the reference op */
+  double bytes;        /* fp32 input + output bytes of the op (no reuse assumed) */
+  float ms;            /* device time between the two events */
+  float reserved;
+} fv_profile_entry;
+int fv_forward_profile(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,
+                       size_t workspace_bytes, int flags, void* stream, fv_profile_entry* entries, int cap,
+                       int* count);
 /* algorithmic FLOPs (2*MAC, dense conv math as the reference executes it) of one fv_forward(B,T) */
 int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops);
 
