@@ -129,7 +129,8 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
     return fail(FV_EINVAL, "ReflectionPad1d needs pad (%d) < length (%lld)", a.pad_left, c.Lin);
   static const bool tc_disabled = getenv("FV_DISABLE_TC") != nullptr;  // operational kill switch
   if (c.allow_tc && !tc_disabled && tcl && tcl->eligible) {
-    int rc = launch_conv_tc(a, *tcl, st);
+    static const bool tc_v1 = getenv("FV_TC_V1") != nullptr;  // previous (non-persistent) kernel, kept for A/B runs
+    int rc = tc_v1 ? launch_conv_tc(a, *tcl, st) : launch_conv_tc2(a, *tcl, st);
     if (rc == 0) {
       if (used_tc) *used_tc = 1;
       return FV_OK;

@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <vector>
@@ -370,7 +371,8 @@ struct TcWeights {
     for (size_t i = 0; i < ls.size(); ++i) {
       const Layer& l = ls[i];
       TcLayer& t = layers[i];
-      const int nt = (l.Cin % 16 == 0) ? tc_pick_nt(l.N) : 0;
+      int nt = (l.Cin % 16 == 0) ? tc_pick_nt(l.N) : 0;
+      if (l.type == L_CONVT && l.Cout % 16) nt = 0;  // a 16-column epilogue chunk must stay inside one phase
       if (nt == 0) continue;
       t.eligible = true;
       t.NT = nt;
@@ -469,6 +471,399 @@ inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) 
   }
   dim3 grid((a.Lpos + p.m_tiles * 128 - 1) / (p.m_tiles * 128), L.n_tiles, a.B);
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  g_launches++;
+  g_tc_launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+
+// =================================================================================================
+// v2: persistent, warp-specialised pipeline
+//   warps 0-7   loaders   : global fp32 -> act/pad -> fp16 hi/lo -> A[stage]          (a_full / a_empty)
+//   warp  8     UMMA issue: tcgen05.mma into accumulator set acc[it % acc_stages]      (acc_full / acc_empty)
+//   warp  9     weights   : cp.async.bulk; whole layer image resident in smem when it fits, else a ring
+//   warps 10-13 epilogue  : tcgen05.ld -> bias/residual/accumulate/tanh -> global      (one TMEM lane quarter each)
+// Each CTA walks tiles (utterance b, time tile) with stride gridDim.x, so the load of tile i+1, the MMAs of
+// tile i and the epilogue of tile i-1 overlap.
+// =================================================================================================
+constexpr int TC2_LOADER_WARPS = 8;
+constexpr int TC2_THREADS = (TC2_LOADER_WARPS + 6) * 32;  // 8 loaders + UMMA + weights + 4 epilogue
+
+struct Tc2Args {
+  ConvArgs a;
+  const uint8_t* wimg;
+  int NT, m_tiles, rows, ksteps, kblocks;
+  int a_stages, acc_stages, w_resident, kb_per_stage, w_stages, stage_bytes;
+  int tmem_cols, acc_cols;
+  int tiles_per_batch, total_tiles;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
+                                                  int nt) {
+  const ConvArgs& a = p.a;
+  float* __restrict__ yb = a.y + (long long)b * a.y_bs;
+  const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
+  const int nchunks = p.NT >> 4;
+  for (int c = 0; c < nchunks; ++c) {
+    const int nbase = nt * p.NT + c * 16;
+    int r = 0, co0 = nbase;
+    if (LAYOUT == OUT_PHASE) { r = nbase / a.ph_cout; co0 = nbase - r * a.ph_cout; }
+    float bias[16];
+    if (a.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + (LAYOUT == OUT_PHASE ? co0 : nbase));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(bp + i);
+        bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+    }
+    for (int mt = 0; mt < p.m_tiles; ++mt) {
+      const int pos = t0 + mt * 128 + q * 32 + lane;
+      uint32_t rr[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT + c * 16), rr);
+      long long o0, ostride;
+      bool ok = pos < a.Lpos;
+      if (LAYOUT == OUT_BCL) {
+        o0 = (long long)nbase * a.Lpos + pos; ostride = a.Lpos;
+      } else if (LAYOUT == OUT_BLC) {
+        o0 = (long long)pos * a.N + nbase; ostride = 1;
+      } else {
+        const int t = pos * a.ph_stride + r - a.ph_pad;
+        ok = ok && t >= 0 && t < a.ph_lout;
+        o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
+      }
+      if (!ok) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias[i];
+      if (rb) {
+        float rv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = __ldg(rb + o0 + i * ostride);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += rv[i];
+      }
+      if (a.acc_mode != ACC_STORE) {
+        float yv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) yv[i] = yb[o0 + i * ostride];
+        if (a.acc_mode == ACC_ADD) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = yv[i] + v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (yv[i] + v[i]) / a.acc_div;
+        }
+      }
+      if (a.post_tanh) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = v[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args p) {
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  const ConvArgs& a = p.a;
+  const int rows = p.rows;
+  const uint32_t a_bytes = (uint32_t)rows * a.Cin * 2;  // hi or lo of one A stage
+  const int kblock_bytes = p.NT * 64;
+  uint8_t* Abuf = smem;                                   // [a_stages][hi|lo][a_bytes]
+  uint8_t* Wbuf = smem + (size_t)p.a_stages * 2 * a_bytes;
+  const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * kblock_bytes : (size_t)p.w_stages * p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wbuf + w_bytes);
+  // barrier map: [0,2) a_full  [2,4) a_empty  [4,6) acc_full  [6,8) acc_empty  [8,16) w_full  [16,24) w_empty
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nt = blockIdx.y;
+  const int M = p.m_tiles * 128;
+  const uint8_t* wsrc = p.wimg + (size_t)nt * p.kblocks * kblock_bytes;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(0 + s), TC2_LOADER_WARPS);   // a_full: one arrive per loader warp
+      mbar_init(BAR(2 + s), 1);   // a_empty: tcgen05.commit
+      mbar_init(BAR(4 + s), 1);   // acc_full: tcgen05.commit
+      mbar_init(BAR(6 + s), 4);   // acc_empty: one arrive per epilogue warp
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(BAR(8 + s), 1);
+      mbar_init(BAR(16 + s), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == TC2_LOADER_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TC2_LOADER_WARPS) {
+    // ------------------------------------------------------------------ loaders
+    const int nkc = a.Cin >> 3;
+    const int nrb = (rows + 127) >> 7;          // row blocks of 128 (4 rows per lane)
+    const int npairs = nkc * nrb;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % p.a_stages;
+      if (it >= p.a_stages) mbar_wait(BAR(2 + s), (uint32_t)((it / p.a_stages - 1) & 1), 400 + s);
+      const int b = tile / p.tiles_per_batch;
+      const int t0 = (tile - b * p.tiles_per_batch) * M;
+      const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
+      uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
+      uint8_t* A_lo = A_hi + a_bytes;
+      for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
+        const int kc = pr / nrb, rbk = pr - kc * nrb;
+        const float* __restrict__ xc = xb + (long long)(kc * 8) * a.Lin;
+        float v[4][8];
+        int rrow[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int r = rbk * 128 + t * 32 + lane;
+          rrow[t] = r;
+          int g = t0 - a.pad_left + r;
+          if (a.pad_mode == PAD_REFLECT) {
+            if (g < 0) g = -g;
+            if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+          }
+          const bool ok = r < rows && g >= 0 && g < a.Lin;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * a.Lin + g) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (rrow[t] >= rows) continue;
+          __half hi[8], lo[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) split_f16(pre_act(v[t][c], a.pre_slope), hi[c], lo[c]);
+          const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
+          *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
+                                                             pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+          *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                                             pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(0 + s));
+    }
+  } else if (warp == TC2_LOADER_WARPS + 1) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      if (p.w_resident) {
+        const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
+        mbar_expect_tx(BAR(8), total);
+        for (uint32_t off = 0; off < total; off += 32768) {
+          const uint32_t n = min(32768u, total - off);
+          bulk_g2s(smem_u32(Wbuf + off), wsrc + off, n, BAR(8));
+        }
+      } else {
+        const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
+        int g = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
+            const int slot = g % p.w_stages;
+            if (g >= p.w_stages) mbar_wait(BAR(16 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 500 + slot);
+            const int kb0 = wi * p.kb_per_stage;
+            const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
+            const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
+            mbar_expect_tx(BAR(8 + slot), bytes);
+            bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
+                     BAR(8 + slot));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == TC2_LOADER_WARPS) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      const uint32_t a_lbo = (uint32_t)rows * 16;
+      const uint32_t b_lbo = (uint32_t)p.NT * 16;
+      const uint32_t wbase = smem_u32(Wbuf);
+      if (p.w_resident) mbar_wait(BAR(8), 0, 600);
+      const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
+      int it = 0, g = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % p.a_stages, as = it % p.acc_stages;
+        mbar_wait(BAR(0 + s), (uint32_t)((it / p.a_stages) & 1), 610 + s);
+        if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
+        tc_fence_after();
+        const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes), a_lo0 = a_hi0 + a_bytes;
+        const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
+        auto do_kblock = [&](int kb, uint32_t bsm) {
+          const int j = kb / p.ksteps, ks = kb - j * p.ksteps;
+          const uint64_t bd_hi = make_kmajor_desc(bsm, b_lbo, 128);
+          const uint64_t bd_lo = make_kmajor_desc(bsm + p.NT * 32, b_lbo, 128);
+          const uint32_t a_k = (uint32_t)(2 * ks) * a_lbo;
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const uint32_t a_off = a_k + (uint32_t)(mt * 128 + j * a.dil) * 16;
+            const uint64_t ad_hi = make_kmajor_desc(a_hi0 + a_off, a_lbo, 128);
+            const uint64_t ad_lo = make_kmajor_desc(a_lo0 + a_off, a_lbo, 128);
+            const uint32_t d = acc + (uint32_t)(mt * p.NT);
+            umma_f16(d, ad_hi, bd_hi, p.idesc, kb > 0 ? 1u : 0u);
+            umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+            umma_f16(d, ad_lo, bd_hi, p.idesc, 1u);
+          }
+        };
+        if (p.w_resident) {
+          for (int kb = 0; kb < p.kblocks; ++kb) do_kblock(kb, wbase + (uint32_t)kb * kblock_bytes);
+        } else {
+          for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
+            const int slot = g % p.w_stages;
+            mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
+            tc_fence_after();
+            const int kb0 = wi * p.kb_per_stage;
+            const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
+            for (int qk = 0; qk < nkb; ++qk)
+              do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
+            umma_commit(BAR(16 + slot));
+          }
+        }
+        umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
+        umma_commit(BAR(4 + as));   // accumulators of this tile complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (4 consecutive warps)
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it % p.acc_stages;
+      mbar_wait(BAR(4 + as), (uint32_t)((it / p.acc_stages) & 1), 700 + as);
+      tc_fence_after();
+      const int b = tile / p.tiles_per_batch;
+      const int t0 = (tile - b * p.tiles_per_batch) * M;
+      const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
+      if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL>(p, acc, q, lane, b, t0, nt);
+      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC>(p, acc, q, lane, b, t0, nt);
+      else tc2_epilogue_tile<OUT_PHASE>(p, acc, q, lane, b, t0, nt);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(6 + as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC2_LOADER_WARPS) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+inline size_t tc2_smem_bytes(const Tc2Args& p) {
+  const size_t a_bytes = (size_t)p.rows * p.a.Cin * 2;
+  const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * p.NT * 64 : (size_t)p.w_stages * p.stage_bytes;
+  return p.a_stages * 2 * a_bytes + w_bytes + 25 * 8;
+}
+
+// Choose tile shape / buffering for one layer launch.  Preference order: weights resident in smem (no L2
+// re-streaming), double-buffered A, as many 128-row M tiles per CTA tile as TMEM (2 accumulator sets) allows.
+inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sms) {
+  const int NT = L.NT;
+  const int halo = (a.K - 1) * a.dil;
+  const int kblock_bytes = NT * 64;
+  const int ksteps = a.Cin / 16;
+  const int kblocks = a.K * ksteps;
+  const long long w_total = (long long)kblocks * kblock_bytes;
+  const long long BUDGET = 225 * 1024;
+  const int need_mt = (a.Lpos + 127) / 128;
+  int kbps = 16384 / kblock_bytes;
+  if (kbps < 1) kbps = 1;
+  if (kbps > kblocks) kbps = kblocks;
+  const int stage_bytes = kbps * kblock_bytes;
+  auto a_stage_bytes = [&](int mt) { return 2LL * (mt * 128 + halo) * a.Cin * 2; };
+  struct Cand { int mt, a_st, res, w_st; double score; };
+  Cand best{0, 0, 0, 0, -1.0};
+  // crude cycle model per CTA tile (positions/cycle is maximised):
+  //   UMMA: 3 passes, each max(math NT/2 cycles, operand fetch (4 KB A + NT*32 B) / 128 B/clk)
+  //   loader ~48 B/clk of fp32 input, weight stream ~28 B/clk from L2 (zero when resident), epilogue ~48 B/clk
+  const double c_mma = std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
+  for (int res = 1; res >= 0; --res) {
+    for (int a_st = 2; a_st >= 1; --a_st) {
+      for (int mt = 8; mt >= 1; --mt) {
+        if (mt * NT > 512) continue;
+        if (mt > need_mt && mt > 1) continue;
+        for (int w_st = (res ? 1 : 4); w_st >= (res ? 1 : 2); --w_st) {
+          const long long wb = res ? w_total : (long long)w_st * stage_bytes;
+          if (a_st * a_stage_bytes(mt) + wb + 256 > BUDGET) continue;
+          const bool acc2 = 2 * mt * NT <= 512;
+          const double t_mma = (double)kblocks * 3.0 * mt * c_mma;
+          const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 48.0 + 900.0;
+          const double t_w = res ? 0.0 : (double)w_total / 28.0 * (w_st >= 4 ? 1.0 : 4.0 / w_st);
+          const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 48.0 + 600.0;
+          const double t_core = std::max(t_mma, t_w);
+          double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
+          t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
+          const double sc = (double)mt * 128.0 / t_tile;
+          if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, sc};
+        }
+      }
+    }
+  }
+  if (best.score < 0) return false;
+  p.a = a;
+  p.NT = NT;
+  p.m_tiles = best.mt;
+  p.rows = best.mt * 128 + halo;
+  p.ksteps = ksteps;
+  p.kblocks = kblocks;
+  p.a_stages = best.a_st;
+  p.w_resident = best.res;
+  p.kb_per_stage = kbps;
+  p.w_stages = best.w_st;
+  p.stage_bytes = stage_bytes;
+  p.acc_cols = best.mt * NT;
+  p.acc_stages = (2 * p.acc_cols <= 512) ? 2 : 1;
+  int cols = 32;
+  while (cols < p.acc_stages * p.acc_cols) cols <<= 1;
+  p.tmem_cols = cols;
+  p.idesc = make_idesc_f16(128, NT);
+  p.tiles_per_batch = (a.Lpos + best.mt * 128 - 1) / (best.mt * 128);
+  p.total_tiles = p.tiles_per_batch * a.B;
+  (void)num_sms;
+  return true;
+}
+
+inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
+  static int num_sms[64] = {};
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!num_sms[dev]) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    num_sms[dev] = prop.multiProcessorCount;
+  }
+  Tc2Args p{};
+  if (!L.eligible || !L.image || !tc2_plan(a, L, p, num_sms[dev])) return 1;
+  p.wimg = L.image;
+  const size_t smem = tc2_smem_bytes(p);
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return -1;
+    attr_set[dev] = true;
+  }
+  int gx = num_sms[dev] / L.n_tiles;
+  if (gx < 1) gx = 1;
+  if (gx > p.total_tiles) gx = p.total_tiles;
+  dim3 grid(gx, L.n_tiles, 1);
+  conv_tc2_kernel<<<grid, TC2_THREADS, smem, st>>>(p);
   g_launches++;
   g_tc_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
