@@ -2,6 +2,7 @@
 // layer graph of fv_model.h and launches the sm_100a kernels.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -183,7 +184,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   const int Be = eff_batch(m, B, flags);
   const size_t each = max_act_floats(m, Be, T);
   const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
-  const size_t need = (5 * each + mel_ext_floats) * sizeof(float);
+  const size_t need = (6 * each + mel_ext_floats) * sizeof(float);
   if (ws_bytes < need) return fail(FV_ENOMEM, "workspace too small: have %zu need %zu", ws_bytes, need);
   float* base = (float*)ws;
   float* bufA = base;
@@ -191,7 +192,8 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   float* bufH = base + 2 * each;
   float* bufU0 = base + 3 * each;
   float* bufU1 = base + 4 * each;
-  float* mel_ext = base + 5 * each;
+  float* bufY = base + 5 * each;
+  float* mel_ext = base + 6 * each;
 
   auto wd = [&](int li) { return h->derived + m.layers[li].wd_offset; };
   auto bias = [&](int li) -> const float* {
@@ -231,63 +233,86 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     lc.pad_mode = m.is_hifi() ? PAD_ZERO : PAD_REFLECT;
     if ((rc = call(m.pre, lc))) return rc;
   }
+  // Each stage runs in micro-batches of utterances sized so that the stage's intermediate tensors (upsampled y,
+  // conv1 output h, unit outputs) stay resident in the 126 MB L2 between the kernel that writes them and the
+  // kernel that reads them; only the stage input / output cross HBM.  Utterances are independent, so this is
+  // pure scheduling (results are bit-identical to whole-batch execution).
+  static const long long l2_budget = []() {
+    const char* e = getenv("FV_L2_BUDGET_MB");
+    return (long long)(e ? atoi(e) : 64) * 1024 * 1024;
+  }();
   for (size_t s = 0; s < m.stages.size(); ++s) {
     const Stage& sg = m.stages[s];
-    {  // LeakyReLU + ConvTranspose1d
-      LayerCall lc;
-      lc.x = cur; lc.y = other; lc.B = Be; lc.Lin = L;
-      lc.pre_slope = m.is_hifi() ? 0.1f : 0.2f;  // LRELU_SLOPE modules.py:9 / negative_slope 0.2 melgan.py:30
-      if ((rc = call(sg.up, lc))) return rc;
-      L = Model::convt_out_len(m.layers[sg.up], L);
-    }
-    std::swap(cur, other);  // cur = upsampled y, other is free
-    if (m.is_hifi()) {
-      // MRF: xs = sum_j resblock_j(y); x = xs / num_kernels (hifigan.py:97-103).  `other` accumulates xs.
-      const int nb = (int)sg.branches.size();
-      for (int j = 0; j < nb; ++j) {
-        const Branch& br = sg.branches[j];
-        const float* bc = cur;
-        const int nu = (int)br.units.size();
-        for (int u = 0; u < nu; ++u) {
-          const bool last = (u == nu - 1);
-          float* dst = last ? other : (u % 2 ? bufU1 : bufU0);
-          int acc = ACC_STORE;
-          float div = 1.f;
-          if (last && j > 0) { acc = (j == nb - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb; }
-          if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
-            LayerCall l1;
-            l1.x = bc; l1.y = bufH; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.1f;
-            if ((rc = call(br.units[u].c1, l1))) return rc;
-            LayerCall l2;
-            l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = Be; l2.Lin = L; l2.pre_slope = 0.1f;
-            l2.acc_mode = acc; l2.acc_div = div;
-            if ((rc = call(br.units[u].c2, l2))) return rc;
-          } else {  // ResBlock2 unit (modules.py:248-251)
-            LayerCall l1;
-            l1.x = bc; l1.y = dst; l1.res = bc; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.1f;
-            l1.acc_mode = acc; l1.acc_div = div;
-            if ((rc = call(br.units[u].c1, l1))) return rc;
+    const Layer& up = m.layers[sg.up];
+    const long long Lout = Model::convt_out_len(up, L);
+    const long long in_per_utt = (long long)up.Cin * L, out_per_utt = (long long)sg.Cout * Lout;
+    long long mb = l2_budget / (4 * out_per_utt * (long long)sizeof(float));
+    if (mb < 1) mb = 1;
+    if (mb > Be) mb = Be;
+    for (int b0 = 0; b0 < Be; b0 += (int)mb) {
+      const int nb = (int)std::min<long long>(mb, Be - b0);
+      const float* x_in_mb = cur + (long long)b0 * in_per_utt;
+      float* s_out = other + (long long)b0 * out_per_utt;   // this micro-batch's slice of the stage output
+      {  // LeakyReLU + ConvTranspose1d
+        LayerCall lc;
+        lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L;
+        lc.pre_slope = m.is_hifi() ? 0.1f : 0.2f;  // LRELU_SLOPE modules.py:9 / negative_slope 0.2 melgan.py:30
+        if ((rc = call(sg.up, lc))) return rc;
+      }
+      if (m.is_hifi()) {
+        // MRF: xs = sum_j resblock_j(y); x = xs / num_kernels (hifigan.py:97-103); s_out accumulates xs.
+        const int nb_br = (int)sg.branches.size();
+        for (int j = 0; j < nb_br; ++j) {
+          const Branch& br = sg.branches[j];
+          const float* bc = bufY;
+          const int nu = (int)br.units.size();
+          for (int u = 0; u < nu; ++u) {
+            const bool last = (u == nu - 1);
+            float* dst = last ? s_out : (u % 2 ? bufU1 : bufU0);
+            int acc = ACC_STORE;
+            float div = 1.f;
+            if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
+            if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
+              LayerCall l1;
+              l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
+              if ((rc = call(br.units[u].c1, l1))) return rc;
+              LayerCall l2;
+              l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.1f;
+              l2.acc_mode = acc; l2.acc_div = div;
+              if ((rc = call(br.units[u].c2, l2))) return rc;
+            } else {  // ResBlock2 unit (modules.py:248-251)
+              LayerCall l1;
+              l1.x = bc; l1.y = dst; l1.res = bc; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
+              l1.acc_mode = acc; l1.acc_div = div;
+              if ((rc = call(br.units[u].c1, l1))) return rc;
+            }
+            bc = dst;
           }
-          bc = dst;
+        }
+      } else {
+        const float* sc_in = bufY;
+        const int ns = (int)sg.stacks.size();
+        if (ns == 0) {
+          FV_CUDA(cudaMemcpyAsync(s_out, bufY, sizeof(float) * (size_t)nb * out_per_utt, cudaMemcpyDeviceToDevice, st));
+        }
+        for (int k = 0; k < ns; ++k) {  // ResidualStack (modules.py:372-382)
+          const Stack& sk = sg.stacks[k];
+          float* dst = (k == ns - 1) ? s_out : (k % 2 ? bufY : bufU1);
+          LayerCall l1;
+          l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT;
+          if ((rc = call(sk.dil_conv, l1))) return rc;
+          LayerCall ls;
+          ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout;
+          if ((rc = call(sk.skip, ls))) return rc;
+          LayerCall l2;
+          l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f;
+          if ((rc = call(sk.conv1x1, l2))) return rc;
+          sc_in = dst;
         }
       }
-      if (nb == 1) {  // xs / 1: nothing to do
-      }
-      std::swap(cur, other);  // cur = xs/num_kernels
-    } else {
-      for (const Stack& sk : sg.stacks) {  // ResidualStack (modules.py:372-382)
-        LayerCall l1;
-        l1.x = cur; l1.y = bufH; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT;
-        if ((rc = call(sk.dil_conv, l1))) return rc;
-        LayerCall ls;
-        ls.x = cur; ls.y = bufU0; ls.B = Be; ls.Lin = L;
-        if ((rc = call(sk.skip, ls))) return rc;
-        LayerCall l2;
-        l2.x = bufH; l2.y = other; l2.res = bufU0; l2.B = Be; l2.Lin = L; l2.pre_slope = 0.2f;
-        if ((rc = call(sk.conv1x1, l2))) return rc;
-        std::swap(cur, other);
-      }
     }
+    L = Lout;
+    std::swap(cur, other);  // cur = stage output
   }
 
   if (m.is_hifi()) {  // F.leaky_relu(x) [slope 0.01!] -> conv_post -> tanh (hifigan.py:104-106)
@@ -456,7 +481,7 @@ int fv_workspace_bytes(const fv_handle* h, int B, int T, size_t* bytes) {
   const int Be = h->model.cfg.kind == FV_BASIS_MELGAN ? B + 1 : B;
   const size_t each = max_act_floats(h->model, Be, T);
   const size_t mel_ext = ((size_t)Be * h->model.cfg.in_channels * T + 63) / 64 * 64;
-  *bytes = (5 * each + mel_ext) * sizeof(float);
+  *bytes = (6 * each + mel_ext) * sizeof(float);
   return FV_OK;
 }
 

@@ -809,7 +809,14 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
           const double t_core = std::max(t_mma, t_w);
           double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
           t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
-          const double sc = (double)mt * 128.0 / t_tile;
+          // wave quantisation of the persistent grid (tiles are uniform, so the last wave may be mostly idle)
+          const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
+          long long gx = std::max(1, num_sms / L.n_tiles);
+          if (gx > tiles) gx = tiles;
+          const long long waves = (tiles + gx - 1) / gx;
+          const double tail_eff = (double)tiles / (double)(waves * gx);
+          const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);   // short sequences waste rows
+          const double sc = useful / t_tile * tail_eff;
           if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, sc};
         }
       }
@@ -835,7 +842,6 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.idesc = make_idesc_f16(128, NT);
   p.tiles_per_batch = (a.Lpos + best.mt * 128 - 1) / (best.mt * 128);
   p.total_tiles = p.tiles_per_batch * a.B;
-  (void)num_sms;
   return true;
 }
 
