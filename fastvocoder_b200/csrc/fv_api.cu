@@ -233,13 +233,13 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     lc.pad_mode = m.is_hifi() ? PAD_ZERO : PAD_REFLECT;
     if ((rc = call(m.pre, lc))) return rc;
   }
-  // Each stage runs in micro-batches of utterances sized so that the stage's intermediate tensors (upsampled y,
-  // conv1 output h, unit outputs) stay resident in the 126 MB L2 between the kernel that writes them and the
-  // kernel that reads them; only the stage input / output cross HBM.  Utterances are independent, so this is
-  // pure scheduling (results are bit-identical to whole-batch execution).
+  // Each stage can run in micro-batches of utterances (FV_L2_BUDGET_MB) sized so that the stage's intermediate
+  // tensors stay resident in the 126 MB L2.  Utterances are independent, so this is pure scheduling.  Measured on
+  // B200 (profiles/r01_notes.md): with one persistent launch per conv the extra ~2000 launches/step cost more
+  // than the L2 hits save (35 -> 66 ms), so the default budget is "whole batch"; the knob stays for fused kernels.
   static const long long l2_budget = []() {
     const char* e = getenv("FV_L2_BUDGET_MB");
-    return (long long)(e ? atoi(e) : 64) * 1024 * 1024;
+    return (long long)(e ? atoi(e) : (1 << 20)) * 1024 * 1024;   // default: off (whole batch per launch)
   }();
   for (size_t s = 0; s < m.stages.size(); ++s) {
     const Stage& sg = m.stages[s];

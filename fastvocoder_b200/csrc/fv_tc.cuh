@@ -47,7 +47,7 @@ struct TcLayer {
 
 struct TcArgs {
   ConvArgs a;
-  const uint8_t* wimg;  // [n_tile][kblock = j*ksteps + ks][hi|lo][kc2][NT][8] fp16
+  const uint8_t* wimg;  // [n_tile][kblock = j*ksteps + ks][kc2][hi|lo][NT][8] fp16
   int NT, m_tiles, rows, ksteps, kblocks;
   int kb_per_stage, stages, stage_bytes;
   int tmem_cols;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs p) 
     if (lane == 0) {
       const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo);
       const uint32_t a_lbo = (uint32_t)rows * 16;  // bytes between the two 8-channel chunks of one K=16 step
-      const uint32_t b_lbo = (uint32_t)p.NT * 16;
+      const uint32_t b_lbo = (uint32_t)p.NT * 32;  // hi and lo rows of one 8-channel chunk are adjacent
       for (int it = 0; it < n_stage_iters; ++it) {
         const int slot = it % p.stages;
         mbar_wait(full0 + 8 * slot, (uint32_t)((it / p.stages) & 1), 200 + slot);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs p) 
           const int kb = kb0 + q;
           const int j = kb / p.ksteps, ks = kb - j * p.ksteps;
           const uint64_t bd_hi = make_kmajor_desc(bs + q * kblock_bytes, b_lbo, 128);
-          const uint64_t bd_lo = make_kmajor_desc(bs + q * kblock_bytes + p.NT * 32, b_lbo, 128);
+          const uint64_t bd_lo = make_kmajor_desc(bs + q * kblock_bytes + p.NT * 16, b_lbo, 128);
           const uint32_t a_k = (uint32_t)(2 * ks) * a_lbo;
           for (int mt = 0; mt < p.m_tiles; ++mt) {
             const uint32_t a_off = a_k + (uint32_t)(mt * 128 + j * a.dil) * 16;
@@ -346,9 +346,9 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __
     const int ks = ci >> 4, kc2 = (ci >> 3) & 1, e = ci & 7;
     const long long kb = (long long)j * ksteps + ks;
     const long long blk = ((long long)nt * Kd * ksteps + kb) * ((long long)NT * 64);
-    const long long off_hi = blk + ((long long)kc2 * NT + nn) * 16 + e * 2;
+    const long long off_hi = blk + ((long long)kc2 * 2 * NT + nn) * 16 + e * 2;   // [kc2][hi|lo][NT][8]
     *reinterpret_cast<__half*>(img + off_hi) = hi;
-    *reinterpret_cast<__half*>(img + off_hi + (long long)NT * 32) = lo;
+    *reinterpret_cast<__half*>(img + off_hi + (long long)NT * 16) = lo;
   }
 }
 
@@ -496,7 +496,9 @@ struct Tc2Args {
   int a_stages, acc_stages, w_resident, kb_per_stage, w_stages, stage_bytes;
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
-  uint32_t idesc;
+  int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
+  uint32_t idesc;    // M=128, N=NT
+  uint32_t idesc2;   // M=128, N=2*NT (dual)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -529,7 +531,14 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
     for (int mt = 0; mt < p.m_tiles; ++mt) {
       const int pos = t0 + mt * 128 + q * 32 + lane;
       uint32_t rr[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT + c * 16), rr);
+      const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
+      tmem_ld16(tcol, rr);
+      if (p.dual) {  // columns [NT, 2NT) hold the separately accumulated hi*lo terms
+        uint32_t r2[16];
+        tmem_ld16(tcol + (uint32_t)p.NT, r2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+      }
       long long o0, ostride;
       bool ok = pos < a.Lpos;
       if (LAYOUT == OUT_BCL) {
@@ -695,32 +704,45 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     // ------------------------------------------------------------------ UMMA issuer
     if (lane == 0) {
       const uint32_t a_lbo = (uint32_t)rows * 16;
-      const uint32_t b_lbo = (uint32_t)p.NT * 16;
+      const uint32_t b_lbo = (uint32_t)p.NT * 32;
       const uint32_t wbase = smem_u32(Wbuf);
       if (p.w_resident) mbar_wait(BAR(8), 0, 600);
       const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
+      // descriptor templates: only the 14-bit start-address field (units of 16 B) changes between UMMAs
+      const uint64_t a_tmpl = make_kmajor_desc(0, a_lbo, 128);
+      const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
+      const uint32_t acc_mt_cols = (uint32_t)(p.NT * (p.dual ? 2 : 1));
       int it = 0, g = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % p.a_stages, as = it % p.acc_stages;
         mbar_wait(BAR(0 + s), (uint32_t)((it / p.a_stages) & 1), 610 + s);
         if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
         tc_fence_after();
-        const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes), a_lo0 = a_hi0 + a_bytes;
+        const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
+        const uint64_t ad_hi_base = a_tmpl + (uint64_t)(a_hi0 >> 4);
+        const uint32_t a_lo_delta = a_bytes >> 4;
         const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
+        int j = 0, ks = 0;   // tap / k-step of the running k-block index (k-blocks are visited in order)
         auto do_kblock = [&](int kb, uint32_t bsm) {
-          const int j = kb / p.ksteps, ks = kb - j * p.ksteps;
-          const uint64_t bd_hi = make_kmajor_desc(bsm, b_lbo, 128);
-          const uint64_t bd_lo = make_kmajor_desc(bsm + p.NT * 32, b_lbo, 128);
-          const uint32_t a_k = (uint32_t)(2 * ks) * a_lbo;
-          for (int mt = 0; mt < p.m_tiles; ++mt) {
-            const uint32_t a_off = a_k + (uint32_t)(mt * 128 + j * a.dil) * 16;
-            const uint64_t ad_hi = make_kmajor_desc(a_hi0 + a_off, a_lbo, 128);
-            const uint64_t ad_lo = make_kmajor_desc(a_lo0 + a_off, a_lbo, 128);
-            const uint32_t d = acc + (uint32_t)(mt * p.NT);
-            umma_f16(d, ad_hi, bd_hi, p.idesc, kb > 0 ? 1u : 0u);
-            umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-            umma_f16(d, ad_lo, bd_hi, p.idesc, 1u);
+          const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
+          const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
+          const uint32_t a_off16 = (uint32_t)(2 * ks) * (uint32_t)rows + (uint32_t)(j * a.dil);   // in 16-B units
+          const uint32_t first = kb > 0 ? 1u : 0u;
+          uint64_t ad_hi = ad_hi_base + a_off16;
+          uint32_t d = acc;
+          if (p.dual) {
+            for (int mt = 0; mt < p.m_tiles; ++mt, ad_hi += 128, d += acc_mt_cols) {
+              umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+              umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+            }
+          } else {
+            for (int mt = 0; mt < p.m_tiles; ++mt, ad_hi += 128, d += acc_mt_cols) {
+              umma_f16(d, ad_hi, bd_hi, p.idesc, first);
+              umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+              umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+            }
           }
+          if (++ks == p.ksteps) { ks = 0; ++j; }
         };
         if (p.w_resident) {
           for (int kb = 0; kb < p.kblocks; ++kb) do_kblock(kb, wbase + (uint32_t)kb * kblock_bytes);
@@ -792,17 +814,20 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   // crude cycle model per CTA tile (positions/cycle is maximised):
   //   UMMA: 3 passes, each max(math NT/2 cycles, operand fetch (4 KB A + NT*32 B) / 128 B/clk)
   //   loader ~48 B/clk of fp32 input, weight stream ~28 B/clk from L2 (zero when resident), epilogue ~48 B/clk
-  const double c_mma = std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
+  const int dualf = (NT <= 128) ? 2 : 1;
+  const double c_mma3 = dualf == 2   // cycles for the 3 logical passes of one k-block on one M tile
+      ? std::max((double)NT, (4096.0 + NT * 64.0) / 128.0) + std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0)
+      : 3.0 * std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
   for (int res = 1; res >= 0; --res) {
     for (int a_st = 2; a_st >= 1; --a_st) {
       for (int mt = 8; mt >= 1; --mt) {
-        if (mt * NT > 512) continue;
+        if (mt * NT * dualf > 512) continue;
         if (mt > need_mt && mt > 1) continue;
         for (int w_st = (res ? 1 : 4); w_st >= (res ? 1 : 2); --w_st) {
           const long long wb = res ? w_total : (long long)w_st * stage_bytes;
           if (a_st * a_stage_bytes(mt) + wb + 256 > BUDGET) continue;
-          const bool acc2 = 2 * mt * NT <= 512;
-          const double t_mma = (double)kblocks * 3.0 * mt * c_mma;
+          const bool acc2 = 2 * mt * NT * dualf <= 512;
+          const double t_mma = (double)kblocks * mt * c_mma3;
           const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 48.0 + 900.0;
           const double t_w = res ? 0.0 : (double)w_total / 28.0 * (w_st >= 4 ? 1.0 : 4.0 / w_st);
           const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 48.0 + 600.0;
@@ -834,12 +859,14 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.kb_per_stage = kbps;
   p.w_stages = best.w_st;
   p.stage_bytes = stage_bytes;
-  p.acc_cols = best.mt * NT;
+  p.dual = dualf == 2 ? 1 : 0;
+  p.acc_cols = best.mt * NT * dualf;
   p.acc_stages = (2 * p.acc_cols <= 512) ? 2 : 1;
   int cols = 32;
   while (cols < p.acc_stages * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.idesc = make_idesc_f16(128, NT);
+  p.idesc2 = make_idesc_f16(128, 2 * NT);
   p.tiles_per_batch = (a.Lpos + best.mt * 128 - 1) / (best.mt * 128);
   p.total_tiles = p.tiles_per_batch * a.B;
   return true;
