@@ -154,6 +154,17 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
+// Two values at once: hi = x with the low 13 mantissa bits cleared (exactly an fp16 value inside the fp16 normal
+// range), lo = fp16(x - hi) where the subtraction is exact in fp32.  hi + lo carries >= 21 mantissa bits, one
+// packed cvt per pair for hi and one for lo (no convert-back).  satfinite clamps |x| > 65504.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  const float l0 = x0 - h0, l1 = x1 - h1;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(h1), "f"(h0));   // d.hi = first src, d.lo = second
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(l1), "f"(l0));
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
@@ -480,14 +491,18 @@ inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) 
 // =================================================================================================
 // v2: persistent, warp-specialised pipeline
 //   warps 0-7   loaders   : global fp32 -> act/pad -> fp16 hi/lo -> A[stage]          (a_full / a_empty)
-//   warp  8     UMMA issue: tcgen05.mma into accumulator set acc[it % acc_stages]      (acc_full / acc_empty)
-//   warp  9     weights   : cp.async.bulk; whole layer image resident in smem when it fits, else a ring
-//   warps 10-13 epilogue  : tcgen05.ld -> bias/residual/accumulate/tanh -> global      (one TMEM lane quarter each)
+//   warps 8-11  UMMA issue: `n_issuers` of them each own the M tiles mt = id, id + n, ... (own accumulators), so
+//                           the scalar issue cost (~60-100 cycles per UMMA) is spread over several threads when
+//                           the UMMAs are short (narrow layers);  tcgen05.commit per issuer    (acc_full / acc_empty)
+//               weights   : warp 11: cp.async.bulk; whole layer image resident in smem when it fits (then warp 11
+//                           may also issue), else a ring it keeps feeding
+//   warps 12-15 epilogue  : tcgen05.ld -> bias/residual/accumulate/tanh -> global      (one TMEM lane quarter each)
 // Each CTA walks tiles (utterance b, time tile) with stride gridDim.x, so the load of tile i+1, the MMAs of
 // tile i and the epilogue of tile i-1 overlap.
 // =================================================================================================
 constexpr int TC2_LOADER_WARPS = 8;
-constexpr int TC2_THREADS = (TC2_LOADER_WARPS + 6) * 32;  // 8 loaders + UMMA + weights + 4 epilogue
+constexpr int TC2_ISSUE_WARPS = 4;    // warps 8..11: UMMA issuers (warp 11 doubles as the weight producer)
+constexpr int TC2_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 4) * 32;  // 8 loaders + 4 issue/producer + 4 epilogue
 
 struct Tc2Args {
   ConvArgs a;
@@ -496,6 +511,7 @@ struct Tc2Args {
   int a_stages, acc_stages, w_resident, kb_per_stage, w_stages, stage_bytes;
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
+  int n_issuers;     // UMMA issuer warps in use (1..4; at most 3 when the weight ring needs warp 11)
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
   uint32_t idesc;    // M=128, N=NT
   uint32_t idesc2;   // M=128, N=2*NT (dual)
@@ -607,13 +623,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(0 + s), TC2_LOADER_WARPS);   // a_full: one arrive per loader warp
-      mbar_init(BAR(2 + s), 1);   // a_empty: tcgen05.commit
-      mbar_init(BAR(4 + s), 1);   // acc_full: tcgen05.commit
+      mbar_init(BAR(2 + s), p.n_issuers);   // a_empty: one tcgen05.commit per issuer
+      mbar_init(BAR(4 + s), p.n_issuers);   // acc_full: one tcgen05.commit per issuer
       mbar_init(BAR(6 + s), 4);   // acc_empty: one arrive per epilogue warp
     }
     for (int s = 0; s < 8; ++s) {
-      mbar_init(BAR(8 + s), 1);
-      mbar_init(BAR(16 + s), 1);
+      mbar_init(BAR(8 + s), 1);                // w_full: expect_tx by the producer
+      mbar_init(BAR(16 + s), p.n_issuers);     // w_empty: one tcgen05.commit per issuer
     }
     fence_mbar_init();
   }
@@ -658,108 +674,109 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (rrow[t] >= rows) continue;
-          __half hi[8], lo[8];
+          uint32_t hp[4], lp[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) split_f16(pre_act(v[t][c], a.pre_slope), hi[c], lo[c]);
+          for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], a.pre_slope), pre_act(v[t][c + 1], a.pre_slope),
+                                                     hp[c >> 1], lp[c >> 1]);
           const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
-          *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
-                                                             pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-          *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                                             pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+          *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(0 + s));
     }
-  } else if (warp == TC2_LOADER_WARPS + 1) {
-    // ------------------------------------------------------------------ weight producer
+  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
+    // ------------------------------------------------------------------ weight producer + UMMA issuers
+    const int wid = warp - TC2_LOADER_WARPS;                 // 0..3
+    const bool is_producer = (wid == TC2_ISSUE_WARPS - 1);
     if (lane == 0) {
-      if (p.w_resident) {
-        const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
-        mbar_expect_tx(BAR(8), total);
-        for (uint32_t off = 0; off < total; off += 32768) {
-          const uint32_t n = min(32768u, total - off);
-          bulk_g2s(smem_u32(Wbuf + off), wsrc + off, n, BAR(8));
-        }
-      } else {
-        const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
-        int g = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-          for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
-            const int slot = g % p.w_stages;
-            if (g >= p.w_stages) mbar_wait(BAR(16 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 500 + slot);
-            const int kb0 = wi * p.kb_per_stage;
-            const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-            const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
-            mbar_expect_tx(BAR(8 + slot), bytes);
-            bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
-                     BAR(8 + slot));
+      const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
+      if (is_producer) {
+        if (p.w_resident) {
+          const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
+          mbar_expect_tx(BAR(8), total);
+          for (uint32_t off = 0; off < total; off += 32768) {
+            const uint32_t n = min(32768u, total - off);
+            bulk_g2s(smem_u32(Wbuf + off), wsrc + off, n, BAR(8));
+          }
+        } else {
+          int g = 0;
+          for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
+              const int slot = g % p.w_stages;
+              if (g >= p.w_stages) mbar_wait(BAR(16 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 500 + slot);
+              const int kb0 = wi * p.kb_per_stage;
+              const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
+              const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
+              mbar_expect_tx(BAR(8 + slot), bytes);
+              bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
+                       BAR(8 + slot));
+            }
           }
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == TC2_LOADER_WARPS) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      const uint32_t a_lbo = (uint32_t)rows * 16;
-      const uint32_t b_lbo = (uint32_t)p.NT * 32;
-      const uint32_t wbase = smem_u32(Wbuf);
-      if (p.w_resident) mbar_wait(BAR(8), 0, 600);
-      const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
-      // descriptor templates: only the 14-bit start-address field (units of 16 B) changes between UMMAs
-      const uint64_t a_tmpl = make_kmajor_desc(0, a_lbo, 128);
-      const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
-      const uint32_t acc_mt_cols = (uint32_t)(p.NT * (p.dual ? 2 : 1));
-      int it = 0, g = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int s = it % p.a_stages, as = it % p.acc_stages;
-        mbar_wait(BAR(0 + s), (uint32_t)((it / p.a_stages) & 1), 610 + s);
-        if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
-        tc_fence_after();
-        const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
-        const uint64_t ad_hi_base = a_tmpl + (uint64_t)(a_hi0 >> 4);
+      if (wid < p.n_issuers) {   // (in ring mode n_issuers <= 3, so the producer never gets here)
+        const uint32_t a_lbo = (uint32_t)rows * 16;
+        const uint32_t b_lbo = (uint32_t)p.NT * 32;
+        const uint32_t wbase = smem_u32(Wbuf);
+        if (p.w_resident) mbar_wait(BAR(8), 0, 600);
+        // descriptor templates: only the 14-bit start-address field (units of 16 B) changes between UMMAs
+        const uint64_t a_tmpl = make_kmajor_desc(0, a_lbo, 128);
+        const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
+        const uint32_t acc_mt_cols = (uint32_t)(p.NT * (p.dual ? 2 : 1));
         const uint32_t a_lo_delta = a_bytes >> 4;
-        const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
-        int j = 0, ks = 0;   // tap / k-step of the running k-block index (k-blocks are visited in order)
-        auto do_kblock = [&](int kb, uint32_t bsm) {
-          const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
-          const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
-          const uint32_t a_off16 = (uint32_t)(2 * ks) * (uint32_t)rows + (uint32_t)(j * a.dil);   // in 16-B units
-          const uint32_t first = kb > 0 ? 1u : 0u;
-          uint64_t ad_hi = ad_hi_base + a_off16;
-          uint32_t d = acc;
-          if (p.dual) {
-            for (int mt = 0; mt < p.m_tiles; ++mt, ad_hi += 128, d += acc_mt_cols) {
-              umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
-              umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+        const uint32_t mt_step16 = 128u * (uint32_t)p.n_issuers;          // A rows between my consecutive M tiles
+        const uint32_t d_step = acc_mt_cols * (uint32_t)p.n_issuers;
+        int it = 0, g = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+          const int s = it % p.a_stages, as = it % p.acc_stages;
+          mbar_wait(BAR(0 + s), (uint32_t)((it / p.a_stages) & 1), 610 + s);
+          if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
+          tc_fence_after();
+          const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
+          const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi0 >> 4) + (uint64_t)(wid * 128);
+          const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols) + (uint32_t)wid * acc_mt_cols;
+          int j = 0, ks = 0;   // tap / k-step of the running k-block index (k-blocks are visited in order)
+          auto do_kblock = [&](int kb, uint32_t bsm) {
+            const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
+            const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
+            const uint32_t a_off16 = (uint32_t)(2 * ks) * (uint32_t)rows + (uint32_t)(j * a.dil);   // 16-B units
+            const uint32_t first = kb > 0 ? 1u : 0u;
+            uint64_t ad_hi = ad_mine + a_off16;
+            uint32_t d = acc;
+            if (p.dual) {
+              for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
+                umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+                umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+              }
+            } else {
+              for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
+                umma_f16(d, ad_hi, bd_hi, p.idesc, first);
+                umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+                umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+              }
             }
+            if (++ks == p.ksteps) { ks = 0; ++j; }
+          };
+          if (p.w_resident) {
+            for (int kb = 0; kb < p.kblocks; ++kb) do_kblock(kb, wbase + (uint32_t)kb * kblock_bytes);
           } else {
-            for (int mt = 0; mt < p.m_tiles; ++mt, ad_hi += 128, d += acc_mt_cols) {
-              umma_f16(d, ad_hi, bd_hi, p.idesc, first);
-              umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-              umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+            for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
+              const int slot = g % p.w_stages;
+              mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
+              tc_fence_after();
+              const int kb0 = wi * p.kb_per_stage;
+              const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
+              for (int qk = 0; qk < nkb; ++qk)
+                do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
+              umma_commit(BAR(16 + slot));
             }
           }
-          if (++ks == p.ksteps) { ks = 0; ++j; }
-        };
-        if (p.w_resident) {
-          for (int kb = 0; kb < p.kblocks; ++kb) do_kblock(kb, wbase + (uint32_t)kb * kblock_bytes);
-        } else {
-          for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
-            const int slot = g % p.w_stages;
-            mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
-            tc_fence_after();
-            const int kb0 = wi * p.kb_per_stage;
-            const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-            for (int qk = 0; qk < nkb; ++qk)
-              do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-            umma_commit(BAR(16 + slot));
-          }
+          umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
+          umma_commit(BAR(4 + as));   // my accumulators of this tile are complete
         }
-        umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
-        umma_commit(BAR(4 + as));   // accumulators of this tile complete
       }
     }
     __syncwarp();
@@ -859,6 +876,12 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.kb_per_stage = kbps;
   p.w_stages = best.w_st;
   p.stage_bytes = stage_bytes;
+  {  // issuers: short UMMAs (narrow N) are issue-bound -> spread M tiles over several issuer warps
+    int ni = best.res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1;
+    if (ni > best.mt) ni = best.mt;
+    if (NT * dualf >= 256 && ni > 2) ni = 2;   // long UMMAs: the tensor pipe, not the issue slot, is the limit
+    p.n_issuers = ni < 1 ? 1 : ni;
+  }
   p.dual = dualf == 2 ? 1 : 0;
   p.acc_cols = best.mt * NT * dualf;
   p.acc_stages = (2 * p.acc_cols <= 512) ? 2 : 1;
