@@ -686,6 +686,21 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(0 + s));
+      // The epilogue of this tile (one or two tiles from now) reads the residual and, for the MRF sum, the running
+      // output.  Its 4 warps cannot keep enough DRAM requests in flight, so the loaders pull those lines into L2 now.
+      if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) {
+        const int lines_per_row = (M * 4 + 127) >> 7;
+        const int total = p.NT * lines_per_row;
+        const int ltid = warp * 32 + lane;
+        for (int i = ltid; i < total; i += TC2_LOADER_WARPS * 32) {
+          const int n = i / lines_per_row, ln = i - n * lines_per_row;
+          const long long pos = (long long)t0 + ln * 32;
+          if (pos >= a.Lpos) continue;
+          const long long o = (long long)(nt * p.NT + n) * a.Lpos + pos;
+          if (a.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (long long)b * a.res_bs + o));
+          if (a.acc_mode != ACC_STORE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + (long long)b * a.y_bs + o));
+        }
+      }
     }
   } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weight producer + UMMA issuers
