@@ -158,12 +158,83 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow-output conv (conv_post 16->1 / 64->4, MelGAN LastLayer 32->1): one thread per output position,
+// all (<= 4) output channels in registers, weights in shared memory, input through L1 (each element is
+// reused by K neighbouring threads).  Pure streaming kernel: 4*Cin bytes in, 4*Cout bytes out per position.
+// ---------------------------------------------------------------------------------------------
+template <int NOUT>
+__global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvArgs a) {
+  extern __shared__ float smem[];   // [Cin][K][NOUT]
+  const int wn = a.Cin * a.K * NOUT;
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) {
+    const int n = i % NOUT, r = i / NOUT;   // derived image is [Cin][K][N]
+    smem[i] = n < a.N ? __ldg(a.w + (long long)r * a.N + n) : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* xb = a.x + (long long)b * a.x_bs;
+  float* yb = a.y + (long long)b * a.y_bs;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.Lpos; t += gridDim.x * blockDim.x) {
+    float acc[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
+    const int g0 = t - a.pad_left;
+    const bool interior = g0 >= 0 && g0 + (a.K - 1) * a.dil < a.Lin;   // no padding involved: skip the checks
+    for (int ci = 0; ci < a.Cin; ++ci) {
+      const float* xr = xb + (long long)ci * a.Lin;
+      const float* wr = smem + ci * a.K * NOUT;
+      if (interior) {
+        for (int j = 0; j < a.K; ++j) {
+          const float xv = pre_act(__ldg(xr + g0 + j * a.dil), a.pre_slope);
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(wr[j * NOUT + n], xv, acc[n]);
+        }
+      } else {
+        for (int j = 0; j < a.K; ++j) {
+          int g = g0 + j * a.dil;
+          if (a.pad_mode == PAD_REFLECT) {
+            if (g < 0) g = -g;
+            if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+          }
+          const float xv = (g >= 0 && g < a.Lin) ? pre_act(__ldg(xr + g), a.pre_slope) : 0.f;
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(wr[j * NOUT + n], xv, acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      if (n >= a.N) break;
+      float v = acc[n] + (a.bias ? __ldg(a.bias + n) : 0.f);
+      if (a.post_tanh) v = tanhf(v);
+      yb[(long long)n * a.Lpos + t] = v;
+    }
+  }
+}
+
+inline bool conv_narrow_ok(const ConvArgs& a) {
+  return a.N <= 4 && a.K <= 16 && a.out_layout == OUT_BCL && a.res == nullptr && a.acc_mode == ACC_STORE &&
+         (size_t)a.Cin * a.K * 4 * sizeof(float) <= 40 * 1024;
+}
+
+inline cudaError_t launch_conv_narrow(const ConvArgs& a, cudaStream_t st) {
+  long long gx = (a.Lpos + 255) / 256;
+  if (gx > 148 * 32) gx = 148 * 32;
+  dim3 grid((unsigned)gx, a.B);
+  if (a.N == 1) conv_narrow_kernel<1><<<grid, 256, (size_t)a.Cin * a.K * 1 * sizeof(float), st>>>(a);
+  else conv_narrow_kernel<4><<<grid, 256, (size_t)a.Cin * a.K * 4 * sizeof(float), st>>>(a);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 inline size_t conv_ffma_smem(int co_t, int K, int dil) {
   int tt = (co_t == 16) ? ConvTile<16>::TT : (co_t == 32) ? ConvTile<32>::TT : ConvTile<64>::TT;
   return (size_t)(8 * (tt + (K - 1) * dil) + 8 * K * co_t) * sizeof(float);
 }
 
 inline cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t st) {
+  if (conv_narrow_ok(a)) return launch_conv_narrow(a, st);
   const int co_t = a.N <= 16 ? 16 : (a.N <= 32 ? 32 : 64);
   const size_t smem = conv_ffma_smem(co_t, a.K, a.dil);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
