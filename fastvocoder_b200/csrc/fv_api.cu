@@ -168,7 +168,7 @@ static int eff_batch(const Model& m, int B, int flags) {
 
 struct Profiler {
   struct Rec {
-    int layer, used_tc;
+    int layer, used_tc;   // used_tc: 0 fp32 conv, 1 tcgen05 conv, 2 tcgen05 fused ResBlock1 unit (layer = conv1, + conv2)
     long long Lin;
     int B;
     cudaEvent_t e0, e1;
@@ -180,7 +180,10 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                         size_t ws_bytes, int flags, cudaStream_t st, Profiler* prof = nullptr) {
   const Model& m = h->model;
   const fv_config& c = m.cfg;
-  const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES);
+  static const bool tc_disabled_env = getenv("FV_DISABLE_TC") != nullptr;
+  static const bool fuse_disabled_env = getenv("FV_NO_FUSE") != nullptr;
+  const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES) && !tc_disabled_env;
+  const bool fuse_ok = !fuse_disabled_env;
   const int Be = eff_batch(m, B, flags);
   const size_t each = max_act_floats(m, Be, T);
   const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
@@ -273,6 +276,27 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
             float div = 1.f;
             if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
             if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
+              if (tc_ok && fuse_ok) {   // one kernel: conv1 -> lrelu -> conv2 -> +x, h stays in shared memory
+                const Layer& la = m.layers[br.units[u].c1];
+                const TcLayer* t1 = tcl(br.units[u].c1);
+                const TcLayer* t2 = tcl(br.units[u].c2);
+                if (t1 && t2) {
+                  Profiler::Rec r{};
+                  if (prof) {
+                    r.layer = br.units[u].c1; r.Lin = Lout; r.B = nb; r.used_tc = 2;
+                    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+                    cudaEventRecord(r.e0, st);
+                  }
+                  const int frc = launch_fused_unit(bc, dst, bias(br.units[u].c1), bias(br.units[u].c2), *t1, *t2, nb,
+                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st);
+                  if (prof) {
+                    if (frc == 0) { cudaEventRecord(r.e1, st); prof->recs.push_back(r); }
+                    else { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+                  }
+                  if (frc < 0) return fail(FV_ECUDA, "fused unit launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                  if (frc == 0) { bc = dst; continue; }
+                }
+              }
               LayerCall l1;
               l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
               if ((rc = call(br.units[u].c1, l1))) return rc;
@@ -516,7 +540,7 @@ int fv_forward_profile(fv_handle* h, const float* mel, int B, int T, float* out,
       o.Cin = l.Cin; o.N = l.N; o.K = l.Kd; o.dil = l.dil;
       o.positions = (int64_t)r.B * r.Lin;
       // algorithmic MACs: every input sample meets every (Cout, tap) of the reference op
-      o.flops = 2.0 * (double)l.Cin * l.Cout * l.K * (double)r.Lin * r.B;
+      o.flops = 2.0 * (double)l.Cin * l.Cout * l.K * (double)r.Lin * r.B * (r.used_tc == 2 ? 2.0 : 1.0);
       // algorithmic HBM bytes if nothing were cached: read x, write y (+ read residual for half the convs, ignored)
       o.bytes = 4.0 * r.B * ((double)l.Cin * r.Lin + (double)l.Cout * (double)layer_out_len(l, r.Lin) /
                                                          (l.type == L_BASIS ? l.Cout : 1));
@@ -575,6 +599,32 @@ int fv_resblock1(const float* x, const float* const* w1, const float* const* b1,
   for (int u = 0; u < num_dilations; ++u) {
     float* dst = pp[(num_dilations - 1 - u) % 2 ? 0 : 1];
     Layer l1 = make_conv_layer(C, C, K, dilations[u]);
+    if (use_tc == 2) {  // fused-unit kernel (conv1 -> lrelu -> conv2 -> +x in one launch)
+      Layer l2f = make_conv_layer(C, C, K, 1);
+      TempW t1, t2;
+      int rc = t1.make(l1, w1[u], st);
+      if (rc) return rc;
+      if ((rc = t2.make(l2f, w2[u], st))) return rc;
+      // one contiguous fp32 derived buffer is what TcWeights::build expects: pack the two images side by side
+      float* both = nullptr;
+      const size_t n1 = (size_t)C * K * C;
+      FV_CUDA(cudaMalloc(&both, 2 * n1 * sizeof(float)));
+      cudaMemcpyAsync(both, t1.p, n1 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      cudaMemcpyAsync(both + n1, t2.p, n1 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      std::vector<Layer> two{l1, l2f};
+      two[0].wd_offset = 0;
+      two[1].wd_offset = (int64_t)n1;
+      TcWeights tcw;
+      int frc = 1;
+      if (tcw.build(two, both, st) == 0 && tcw.layer(0) && tcw.layer(1))
+        frc = launch_fused_unit(cur, dst, b1 ? b1[u] : nullptr, b2 ? b2[u] : nullptr, *tcw.layer(0), *tcw.layer(1), B, C,
+                                L, K, dilations[u], 0.1f, ACC_STORE, 1.f, st);
+      cudaError_t se = cudaStreamSynchronize(st);
+      cudaFree(both);
+      tcw.release();
+      if (frc < 0 || se != cudaSuccess) return fail(FV_ECUDA, "fused unit failed: %s", cudaGetErrorString(se));
+      if (frc == 0) { cur = dst; continue; }
+    }
     LayerCall c1;
     c1.x = cur; c1.y = hbuf; c1.B = B; c1.Lin = L; c1.pre_slope = 0.1f;
     int rc = conv_raw(l1, w1[u], b1 ? b1[u] : nullptr, c1, use_tc, st);

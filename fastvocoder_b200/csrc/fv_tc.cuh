@@ -943,4 +943,376 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+
+// =================================================================================================
+// v3: fused ResBlock1 unit (modules.py:224-229)
+//        y = conv2( lrelu( conv1_dil(lrelu(x)) + b1 ) ) + b2 + x          [+ MRF accumulate]
+// in ONE persistent kernel: the intermediate h never leaves the SM.  conv1's accumulators are read back by the
+// epilogue warps, biased, activated, split to fp16 hi/lo and written straight into shared memory in the UMMA
+// operand layout (A2); conv2 then runs on A2.  Per unit this moves 4C B in + 4C B out (+4C accumulate) per
+// position instead of 4C·5 (+4C) for the two-kernel form — the narrow layers were DRAM-bound on exactly that.
+// Both weight images stay resident in shared memory (C <= 64).  Tile: 128m rows of h -> M_out = 128m-(K-1)
+// outputs (conv2's halo is recomputed), x rows = 128m + (K-1)*dil.
+// =================================================================================================
+struct Tc3Args {
+  const float* x;      // unit input [B, C, L] (also the residual)
+  float* y;            // [B, C, L]
+  const float* bias1;  // conv1 bias or nullptr
+  const float* bias2;
+  const uint8_t* w1img;
+  const uint8_t* w2img;
+  int B, C, L, K, dil;
+  float slope;         // LeakyReLU slope applied to x and to h (0.1)
+  int acc_mode;
+  float acc_div;
+  int m_tiles, x_rows, h_rows_alloc, m_out;
+  int a1_stages, acc1_stages, n_issuers;
+  int acc_cols;        // columns of one accumulator set = m_tiles * 2C
+  int tmem_cols;
+  int ksteps, kblocks;
+  int tiles_per_batch, total_tiles;
+  uint32_t idesc, idesc2;
+};
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p) {
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  const int C = p.C, NT = p.C;
+  const uint32_t a1_bytes = (uint32_t)p.x_rows * C * 2;        // hi or lo of one A1 stage
+  const uint32_t a2_bytes = (uint32_t)p.h_rows_alloc * C * 2;  // hi or lo of A2
+  const int kblock_bytes = NT * 64;
+  const uint32_t w_bytes = (uint32_t)p.kblocks * kblock_bytes;
+  uint8_t* A1 = smem;                                            // [a1_stages][hi|lo]
+  uint8_t* A2 = A1 + (size_t)p.a1_stages * 2 * a1_bytes;        // [hi|lo]
+  uint8_t* W1 = A2 + 2 * (size_t)a2_bytes;
+  uint8_t* W2 = W1 + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W2 + w_bytes);
+  // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  10 acc2_full  11 acc2_empty  12 w_full
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(0 + s), TC2_LOADER_WARPS);
+      mbar_init(BAR(2 + s), p.n_issuers);
+      mbar_init(BAR(4 + s), p.n_issuers);
+      mbar_init(BAR(6 + s), 4);
+    }
+    mbar_init(BAR(8), 4);
+    mbar_init(BAR(9), p.n_issuers);
+    mbar_init(BAR(10), p.n_issuers);
+    mbar_init(BAR(11), 4);
+    mbar_init(BAR(12), 1);
+    fence_mbar_init();
+  }
+  if (warp == TC2_LOADER_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);
+
+  if (warp < TC2_LOADER_WARPS) {
+    // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
+    const int rows = p.x_rows;
+    const int nkc = C >> 3;
+    const int nrb = (rows + 127) >> 7;
+    const int npairs = nkc * nrb;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % p.a1_stages;
+      if (it >= p.a1_stages) mbar_wait(BAR(2 + s), (uint32_t)((it / p.a1_stages - 1) & 1), 800 + s);
+      const int b = tile / p.tiles_per_batch;
+      const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
+      const float* __restrict__ xb = p.x + (long long)b * C * p.L;
+      uint8_t* A_hi = A1 + (size_t)s * 2 * a1_bytes;
+      uint8_t* A_lo = A_hi + a1_bytes;
+      for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
+        const int kc = pr / nrb, rbk = pr - kc * nrb;
+        const float* __restrict__ xc = xb + (long long)(kc * 8) * p.L;
+        float v[4][8];
+        int rrow[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int r = rbk * 128 + t * 32 + lane;
+          rrow[t] = r;
+          const int g = t0 - p2 - p1 + r;
+          const bool ok = r < rows && g >= 0 && g < p.L;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * p.L + g) : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (rrow[t] >= rows) continue;
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int c = 0; c < 8; c += 2)
+            split_f16x2(pre_act(v[t][c], p.slope), pre_act(v[t][c + 1], p.slope), hp[c >> 1], lp[c >> 1]);
+          const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
+          *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(0 + s));
+    }
+  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
+    // ------------------------------------------------------------------ weights (once) + UMMA issuers
+    const int wid = warp - TC2_LOADER_WARPS;
+    if (lane == 0) {
+      if (wid == TC2_ISSUE_WARPS - 1) {
+        mbar_expect_tx(BAR(12), 2 * w_bytes);
+        for (uint32_t off = 0; off < w_bytes; off += 32768) {
+          const uint32_t n = min(32768u, w_bytes - off);
+          bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(12));
+          bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(12));
+        }
+      }
+      if (wid < p.n_issuers) {
+        mbar_wait(BAR(12), 0, 810);
+        const uint32_t b_lbo = (uint32_t)NT * 32;
+        const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
+        const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows * 16, 128);
+        const uint64_t a2_tmpl = make_kmajor_desc(0, (uint32_t)p.h_rows_alloc * 16, 128);
+        const uint32_t mt_cols = (uint32_t)(2 * NT);
+        const uint32_t mt_step16 = 128u * (uint32_t)p.n_issuers;
+        const uint32_t d_step = mt_cols * (uint32_t)p.n_issuers;
+        const uint32_t w1s = smem_u32(W1), w2s = smem_u32(W2);
+        // one GEMM-conv over a resident weight image: A rows [row0 + j*dil], accumulators at `acc`
+        auto run_conv = [&](uint64_t a_tmpl, uint32_t a_hi_addr, uint32_t a_rows, uint32_t a_lo_delta16, uint32_t wsm,
+                            int dil, uint32_t acc) {
+          const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi_addr >> 4) + (uint64_t)(wid * 128);
+          int j = 0, ks = 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const uint64_t bd_hi = b_tmpl + (uint64_t)((wsm + (uint32_t)kb * kblock_bytes) >> 4);
+            const uint32_t a_off16 = (uint32_t)(2 * ks) * a_rows + (uint32_t)(j * dil);
+            const uint32_t first = kb > 0 ? 1u : 0u;
+            uint64_t ad_hi = ad_mine + a_off16;
+            uint32_t d = acc + (uint32_t)wid * mt_cols;
+            for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
+              umma_f16(d, ad_hi, bd_hi, p.idesc2, first);
+              umma_f16(d, ad_hi + a_lo_delta16, bd_hi, p.idesc, 1u);
+            }
+            if (++ks == p.ksteps) { ks = 0; ++j; }
+          }
+        };
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) ++n_my;
+        auto conv1 = [&](int i) {
+          const int s = i % p.a1_stages, as = i % p.acc1_stages;
+          mbar_wait(BAR(0 + s), (uint32_t)((i / p.a1_stages) & 1), 820 + s);
+          if (i >= p.acc1_stages) mbar_wait(BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
+          tc_fence_after();
+          run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w1s, p.dil,
+                   tmem_base + (uint32_t)(as * p.acc_cols));
+          umma_commit(BAR(2 + s));
+          umma_commit(BAR(4 + as));
+        };
+        auto conv2 = [&](int i) {
+          mbar_wait(BAR(8), (uint32_t)(i & 1), 840);
+          if (i >= 1) mbar_wait(BAR(11), (uint32_t)((i - 1) & 1), 850);
+          tc_fence_after();
+          run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1, acc2_base);
+          umma_commit(BAR(9));
+          umma_commit(BAR(10));
+        };
+        if (n_my > 0) conv1(0);
+        for (int i = 0; i < n_my; ++i) {
+          if (i + 1 < n_my) conv1(i + 1);
+          conv2(i);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps: epiA (-> A2) and epiB (-> global)
+    const int q = warp & 3;
+    const int nchunks = NT >> 4;
+    uint8_t* A2_hi = A2;
+    uint8_t* A2_lo = A2 + a2_bytes;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_batch;
+      const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
+      {  // ---- epiA: acc1 -> +b1 -> lrelu -> fp16 split -> A2 (zero rows outside the sequence: conv2's zero padding)
+        const int as = it % p.acc1_stages;
+        mbar_wait(BAR(4 + as), (uint32_t)((it / p.acc1_stages) & 1), 860 + as);
+        if (it >= 1) mbar_wait(BAR(9), (uint32_t)((it - 1) & 1), 870);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+          const int r = mt * 128 + q * 32 + lane;
+          const int gpos = t0 - p2 + r;
+          const bool inside = gpos >= 0 && gpos < p.L;
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t rr[16], r2[16];
+            const uint32_t tcol = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
+            tmem_ld16(tcol, rr);
+            tmem_ld16(tcol + (uint32_t)NT, r2);
+            uint32_t hp[8], lp[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]);
+              float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]);
+              if (p.bias1) { v0 += __ldg(p.bias1 + c * 16 + i); v1 += __ldg(p.bias1 + c * 16 + i + 1); }
+              v0 = inside ? pre_act(v0, p.slope) : 0.f;
+              v1 = inside ? pre_act(v1, p.slope) : 0.f;
+              split_f16x2(v0, v1, hp[i >> 1], lp[i >> 1]);
+            }
+            const uint32_t off0 = ((uint32_t)(2 * c) * p.h_rows_alloc + r) * 16;
+            const uint32_t off1 = ((uint32_t)(2 * c + 1) * p.h_rows_alloc + r) * 16;
+            *reinterpret_cast<uint4*>(A2_hi + off0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(A2_hi + off1) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+            *reinterpret_cast<uint4*>(A2_lo + off0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            *reinterpret_cast<uint4*>(A2_lo + off1) = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(BAR(6 + as));   // acc1 set drained
+          mbar_arrive(BAR(8));        // A2 ready for conv2
+        }
+      }
+      {  // ---- epiB: acc2 -> +b2 + x (+ MRF accumulate) -> y
+        mbar_wait(BAR(10), (uint32_t)(it & 1), 880);
+        tc_fence_after();
+        const float* __restrict__ xb = p.x + (long long)b * C * p.L;
+        float* __restrict__ yb = p.y + (long long)b * C * p.L;
+        const float inv = 1.0f / p.acc_div;
+        for (int c = 0; c < nchunks; ++c) {
+          float bias[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bias[i] = p.bias2 ? __ldg(p.bias2 + c * 16 + i) : 0.f;
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const int r = mt * 128 + q * 32 + lane;
+            const int t = t0 + r;
+            uint32_t rr[16], r2[16];
+            const uint32_t tcol = acc2_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
+            tmem_ld16(tcol, rr);
+            tmem_ld16(tcol + (uint32_t)NT, r2);
+            if (r >= p.m_out || t >= p.L) continue;
+            const long long o0 = (long long)(c * 16) * p.L + t;
+            float v[16], xv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xv[i] = __ldg(xb + o0 + (long long)i * p.L);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              v[i] = (__uint_as_float(rr[i]) + __uint_as_float(r2[i]) + bias[i]) + xv[i];
+            if (p.acc_mode != ACC_STORE) {
+              float yv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) yv[i] = yb[o0 + (long long)i * p.L];
+              if (p.acc_mode == ACC_ADD) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = yv[i] + v[i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (yv[i] + v[i]) * inv;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) yb[o0 + (long long)i * p.L] = v[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(11));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC2_LOADER_WARPS) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+inline size_t tc3_smem_bytes(const Tc3Args& p) {
+  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + 2ULL * p.h_rows_alloc * p.C * 2 +
+         2ULL * p.kblocks * p.C * 64 + 14 * 8;
+}
+
+// conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64)
+inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
+  if (C % 16 || C > 64 || K % 2 == 0) return false;
+  const int ksteps = C / 16, kblocks = K * ksteps;
+  const long long BUDGET = 225 * 1024;
+  int best_m = 0, best_a1 = 0, best_acc1 = 0;
+  double best_sc = -1;
+  for (int acc1 = 2; acc1 >= 1; --acc1)
+    for (int a1 = 2; a1 >= 1; --a1)
+      for (int m = 8; m >= 1; --m) {
+        if ((acc1 + 1) * m * 2 * C > 512) continue;
+        const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
+        const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + 2LL * kblocks * C * 64 + 256;
+        if (sm > BUDGET) continue;
+        const int m_out = 128 * m - (K - 1);
+        if (m_out <= 0) continue;
+        const long long tiles = (long long)((L + m_out - 1) / m_out) * B;
+        const long long gx = std::min<long long>(148, tiles);
+        const long long waves = (tiles + gx - 1) / gx;
+        const double tail = (double)tiles / (double)(waves * gx);
+        double sc = (double)m_out / (128.0 * m) * tail;          // useful fraction of computed rows x wave balance
+        sc *= (a1 == 2 ? 1.0 : 0.8) * (acc1 == 2 ? 1.0 : 0.85);  // overlap bonuses
+        sc *= (m >= 2 ? 1.0 : 0.9);
+        if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; }
+      }
+  if (best_sc < 0) return false;
+  p.B = B; p.C = C; p.L = L; p.K = K; p.dil = dil;
+  p.m_tiles = best_m;
+  p.x_rows = 128 * best_m + (K - 1) * dil;
+  p.h_rows_alloc = 128 * best_m + (K - 1);
+  p.m_out = 128 * best_m - (K - 1);
+  p.a1_stages = best_a1;
+  p.acc1_stages = best_acc1;
+  p.n_issuers = std::min(best_m, TC2_ISSUE_WARPS);
+  p.acc_cols = best_m * 2 * C;
+  int cols = 32;
+  while (cols < (best_acc1 + 1) * p.acc_cols) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ksteps = ksteps;
+  p.kblocks = kblocks;
+  p.tiles_per_batch = (L + p.m_out - 1) / p.m_out;
+  p.total_tiles = p.tiles_per_batch * B;
+  p.idesc = make_idesc_f16(128, C);
+  p.idesc2 = make_idesc_f16(128, 2 * C);
+  return true;
+}
+
+// returns 0 launched, 1 not applicable, -1 CUDA error
+inline int launch_fused_unit(const float* x, float* y, const float* b1, const float* b2, const TcLayer& l1,
+                             const TcLayer& l2, int B, int C, int L, int K, int dil, float slope, int acc_mode,
+                             float acc_div, cudaStream_t st) {
+  if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
+  Tc3Args p{};
+  if (!tc3_plan(B, C, L, K, dil, p)) return 1;
+  p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2;
+  p.w1img = l1.image; p.w2img = l2.image;
+  p.slope = slope; p.acc_mode = acc_mode; p.acc_div = acc_div;
+  static bool attr_set[64] = {};
+  static int num_sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!attr_set[dev]) {
+    if (cudaFuncSetAttribute(conv_tc3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return -1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+    num_sms[dev] = prop.multiProcessorCount;
+    attr_set[dev] = true;
+  }
+  int gx = std::min(num_sms[dev], p.total_tiles);
+  conv_tc3_fused_kernel<<<gx, TC2_THREADS, tc3_smem_bytes(p), st>>>(p);
+  g_launches++;
+  g_tc_launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 }  // namespace fv

@@ -134,7 +134,7 @@ int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* 
  * device time.  Synchronises the stream.  bench.py uses it for the live roofline numbers. */
 typedef struct fv_profile_entry {
   char name[64];       /* parameter name of the layer's weight, e.g. "resblocks.2.convs1.1.weight" */
-  int32_t kernel;      /* 0 fp32 FFMA conv, 1 tcgen05 split-fp16 conv */
+  int32_t kernel;      /* 0 fp32 FFMA conv, 1 tcgen05 split-fp16 conv, 2 tcgen05 fused ResBlock1 unit (conv1+conv2) */
   int32_t Cin, N, K, dil;
   int64_t positions;   /* B * input length */
   double flops;        /* 2 * MAC of the reference op */
@@ -151,7 +151,7 @@ int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops)
 /* ---- per-op entry points (unit parity tests; reference layouts, weights passed raw) ---------------
  * All pointers are device pointers.  `pad_mode`: 0 zero, 1 reflect.  `pre_slope` < 0 disables the
  * LeakyReLU applied to the input before the convolution (0 = ReLU).  `residual` may be NULL.
- * `use_tc` != 0 routes through the tcgen05 path when the shape is eligible.
+ * `use_tc` != 0 routes through the tcgen05 path when the shape is eligible (fv_resblock1: 2 = fused-unit kernel).
  *
  * fv_conv1d            <- torch.nn.Conv1d call sites (modules.py:193-220,364,366,377; hifigan.py:93,105)
  * fv_conv_transpose1d  <- torch.nn.ConvTranspose1d call sites (hifigan.py:39-44, melgan.py:77-85)

@@ -415,6 +415,38 @@ def test_tc_conv_transpose_shapes(Cin, Cout, k, s, Lin):
     assert np.abs(got - want).max() < 2e-5
 
 
+@pytest.mark.parametrize("C,K,L", [(16, 3, 700), (16, 11, 2100), (32, 7, 1000), (32, 11, 333), (64, 3, 400),
+                                   (16, 7, 60), (48, 3, 130)])
+def test_fused_resblock1_unit_kernel(C, K, L):
+    """conv1 -> LeakyReLU -> conv2 -> +x fused in one tcgen05 kernel (h stays in shared memory) vs the oracle."""
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    rng = np.random.default_rng(C * 100 + K)
+    B, dil = 2, (1, 3, 5)
+    x = rng.standard_normal((B, C, L)).astype(np.float32)
+    params = {}
+    for i in range(3):
+        for nm in ("convs1", "convs2"):
+            params[f"rb.{nm}.{i}.weight"] = (rng.standard_normal((C, C, K)) * (0.6 / np.sqrt(C * K))).astype(np.float32)
+            params[f"rb.{nm}.{i}.bias"] = (rng.standard_normal(C) * 0.1).astype(np.float32)
+    want = O.resblock1(x.astype(np.float64), {k: v.astype(np.float64) for k, v in params.items()}, "rb", K, dil)
+    w1 = [dev(params[f"rb.convs1.{i}.weight"]) for i in range(3)]
+    b1 = [dev(params[f"rb.convs1.{i}.bias"]) for i in range(3)]
+    w2 = [dev(params[f"rb.convs2.{i}.weight"]) for i in range(3)]
+    b2 = [dev(params[f"rb.convs2.{i}.bias"]) for i in range(3)]
+    dilc = (C.c_int * 3)(*dil) if False else None
+    import ctypes
+    dilc = (ctypes.c_int * 3)(*dil)
+    y = torch.empty(B, C, L, device="cuda")
+    scratch = torch.empty(2 * B * C * L, device="cuda")
+    dx = dev(x)
+    n0 = _lib.lib().fv_launch_count()
+    _lib.check(_lib.lib().fv_resblock1(_lib.ptr(dx), _ptr_array(w1), _ptr_array(b1), _ptr_array(w2), _ptr_array(b2), dilc,
+                                       3, _lib.ptr(y), _lib.ptr(scratch), B, C, L, K, 2, stream()))
+    err = np.abs(y.cpu().numpy() - want).max()
+    assert err < 2e-5, err
+
+
 def test_oversized_layer_falls_back_to_exact_fp32_kernel():
     """Cin = 512 does not fit the activation tile in shared memory: the library must run the CUDA-core kernel."""
     rng = np.random.default_rng(1)
