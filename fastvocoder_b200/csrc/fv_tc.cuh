@@ -954,6 +954,8 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
 // Both weight images stay resident in shared memory (C <= 64).  Tile: 128m rows of h -> M_out = 128m-(K-1)
 // outputs (conv2's halo is recomputed), x rows = 128m + (K-1)*dil.
 // =================================================================================================
+constexpr int TC3_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 8) * 32;   // + 4 epiA warps + 4 epiB warps
+
 struct Tc3Args {
   const float* x;      // unit input [B, C, L] (also the residual)
   float* y;            // [B, C, L]
@@ -974,7 +976,7 @@ struct Tc3Args {
   uint32_t idesc, idesc2;
 };
 
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p) {
+__global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
   const int C = p.C, NT = p.C;
@@ -1129,8 +1131,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fused_kernel(const Tc
       }
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue warps: epiA (-> A2) and epiB (-> global)
+  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 4) {
+    // ------------------------------------------------------------------ epiA warps: acc1 -> A2 (shared memory)
     const int q = warp & 3;
     const int nchunks = NT >> 4;
     uint8_t* A2_hi = A2;
@@ -1180,6 +1182,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc3_fused_kernel(const Tc
           mbar_arrive(BAR(8));        // A2 ready for conv2
         }
       }
+    }
+  } else {
+    // ------------------------------------------------------------------ epiB warps: acc2 -> global
+    const int q = warp & 3;
+    const int nchunks = NT >> 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.tiles_per_batch;
+      const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       {  // ---- epiB: acc2 -> +b2 + x (+ MRF accumulate) -> y
         mbar_wait(BAR(10), (uint32_t)(it & 1), 880);
         tc_fence_after();
@@ -1309,7 +1320,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     attr_set[dev] = true;
   }
   int gx = std::min(num_sms[dev], p.total_tiles);
-  conv_tc3_fused_kernel<<<gx, TC2_THREADS, tc3_smem_bytes(p), st>>>(p);
+  conv_tc3_fused_kernel<<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
   g_launches++;
   g_tc_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -471,7 +471,7 @@ def test_model_uses_tensor_cores_when_enabled(specs):
     t0 = _lib.lib().fv_tc_launch_count()
     m(mel)
     used = _lib.lib().fv_tc_launch_count() - t0
-    assert used >= 70, used            # 72 ResBlock convs + conv_pre + 4 upsamplers are eligible
+    assert used >= 40, used            # conv_pre + 4 upsamplers + 36 fused ResBlock units (or 72 convs unfused)
     m.use_tensor_cores = False
     t0 = _lib.lib().fv_tc_launch_count()
     m(mel)
