@@ -34,8 +34,9 @@ struct ConvArgs {
   long long x_bs, y_bs, res_bs;  // batch strides in floats
 };
 
+// LeakyReLU with 0 <= slope <= 1 (slope 0 = ReLU) is max(v, slope*v); slope < 0 means "no activation".
 __device__ __forceinline__ float pre_act(float v, float slope) {
-  return (slope >= 0.f && v < 0.f) ? v * slope : v;
+  return slope >= 0.f ? fmaxf(v, v * slope) : v;
 }
 
 // ---------------------------------------------------------------------------------------------

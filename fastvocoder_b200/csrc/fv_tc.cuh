@@ -69,10 +69,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: sleep, do not poll
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -989,10 +989,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   uint8_t* W1 = A2 + 2 * (size_t)a2_bytes;
   uint8_t* W2 = W1 + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(W2 + w_bytes);
-  // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  10 acc2_full  11 acc2_empty  12 w_full
+  // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  [10,12) acc2_full  [12,14) acc2_empty  14 w_full
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
@@ -1006,9 +1006,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     }
     mbar_init(BAR(8), 4);
     mbar_init(BAR(9), p.n_issuers);
-    mbar_init(BAR(10), p.n_issuers);
-    mbar_init(BAR(11), 4);
-    mbar_init(BAR(12), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(10 + s), p.n_issuers);
+      mbar_init(BAR(12 + s), 4);
+    }
+    mbar_init(BAR(14), 1);
     fence_mbar_init();
   }
   if (warp == TC2_LOADER_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -1016,7 +1018,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);
+  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);   // two acc2 sets follow
 
   if (warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
@@ -1068,15 +1070,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     const int wid = warp - TC2_LOADER_WARPS;
     if (lane == 0) {
       if (wid == TC2_ISSUE_WARPS - 1) {
-        mbar_expect_tx(BAR(12), 2 * w_bytes);
+        mbar_expect_tx(BAR(14), 2 * w_bytes);
         for (uint32_t off = 0; off < w_bytes; off += 32768) {
           const uint32_t n = min(32768u, w_bytes - off);
-          bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(12));
-          bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(12));
+          bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(14));
+          bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
         }
       }
       if (wid < p.n_issuers) {
-        mbar_wait(BAR(12), 0, 810);
+        mbar_wait(BAR(14), 0, 810);
         const uint32_t b_lbo = (uint32_t)NT * 32;
         const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
         const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows * 16, 128);
@@ -1116,12 +1118,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           umma_commit(BAR(4 + as));
         };
         auto conv2 = [&](int i) {
+          const int bs = i & 1;   // acc2 is double buffered: epiB(i-1) overlaps conv2(i)
           mbar_wait(BAR(8), (uint32_t)(i & 1), 840);
-          if (i >= 1) mbar_wait(BAR(11), (uint32_t)((i - 1) & 1), 850);
+          if (i >= 2) mbar_wait(BAR(12 + bs), (uint32_t)((i / 2 - 1) & 1), 850 + bs);
           tc_fence_after();
-          run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1, acc2_base);
+          run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1,
+                   acc2_base + (uint32_t)(bs * p.acc_cols));
           umma_commit(BAR(9));
-          umma_commit(BAR(10));
+          umma_commit(BAR(10 + bs));
         };
         if (n_my > 0) conv1(0);
         for (int i = 0; i < n_my; ++i) {
@@ -1192,11 +1196,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       {  // ---- epiB: acc2 -> +b2 + x (+ MRF accumulate) -> y
-        mbar_wait(BAR(10), (uint32_t)(it & 1), 880);
-        tc_fence_after();
+        const int bs = it & 1;
         const float* __restrict__ xb = p.x + (long long)b * C * p.L;
         float* __restrict__ yb = p.y + (long long)b * C * p.L;
         const float inv = 1.0f / p.acc_div;
+        const uint32_t acc2 = acc2_base + (uint32_t)(bs * p.acc_cols);
+        bool waited = false;
         for (int c = 0; c < nchunks; ++c) {
           float bias[16];
 #pragma unroll
@@ -1204,15 +1209,23 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           for (int mt = 0; mt < p.m_tiles; ++mt) {
             const int r = mt * 128 + q * 32 + lane;
             const int t = t0 + r;
+            const bool ok = r < p.m_out && t < p.L;
+            const long long o0 = (long long)(c * 16) * p.L + t;
+            // the residual does not depend on the accumulators: issue its loads before waiting for the UMMAs
+            float xv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(xb + o0 + (long long)i * p.L) : 0.f;
+            if (!waited) {
+              mbar_wait(BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
+              tc_fence_after();
+              waited = true;
+            }
             uint32_t rr[16], r2[16];
-            const uint32_t tcol = acc2_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
+            const uint32_t tcol = acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
             tmem_ld16(tcol, rr);
             tmem_ld16(tcol + (uint32_t)NT, r2);
-            if (r >= p.m_out || t >= p.L) continue;
-            const long long o0 = (long long)(c * 16) * p.L + t;
-            float v[16], xv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xv[i] = __ldg(xb + o0 + (long long)i * p.L);
+            if (!ok) continue;
+            float v[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               v[i] = (__uint_as_float(rr[i]) + __uint_as_float(r2[i]) + bias[i]) + xv[i];
@@ -1234,7 +1247,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(11));
+        if (lane == 0) mbar_arrive(BAR(12 + bs));
       }
     }
   }
@@ -1245,7 +1258,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 
 inline size_t tc3_smem_bytes(const Tc3Args& p) {
   return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + 2ULL * p.h_rows_alloc * p.C * 2 +
-         2ULL * p.kblocks * p.C * 64 + 14 * 8;
+         2ULL * p.kblocks * p.C * 64 + 16 * 8;
 }
 
 // conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64)
@@ -1258,7 +1271,7 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   for (int acc1 = 2; acc1 >= 1; --acc1)
     for (int a1 = 2; a1 >= 1; --a1)
       for (int m = 8; m >= 1; --m) {
-        if ((acc1 + 1) * m * 2 * C > 512) continue;
+        if ((acc1 + 2) * m * 2 * C > 512) continue;
         const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
         const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + 2LL * kblocks * C * 64 + 256;
         if (sm > BUDGET) continue;
@@ -1284,7 +1297,7 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   p.n_issuers = std::min(best_m, TC2_ISSUE_WARPS);
   p.acc_cols = best_m * 2 * C;
   int cols = 32;
-  while (cols < (best_acc1 + 1) * p.acc_cols) cols <<= 1;
+  while (cols < (best_acc1 + 2) * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.ksteps = ksteps;
   p.kblocks = kblocks;
