@@ -285,16 +285,36 @@ def main():
         total_ms = sum(k["ms"] for k in by_kernel.values())
         dom = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
         d = by_kernel[dom]
+        kernel_names = {"tcgen05": "conv_tc2_kernel (tcgen05, split-fp16 x3, persistent warp-specialised)",
+                        "tcgen05-fused-unit": "conv_tc3_fused_kernel (tcgen05 fused ResBlock1 unit: conv1+lrelu+conv2+residual)",
+                        "ffma": "conv_ffma_kernel (fp32 CUDA cores)"}
         achieved_tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
         peak_tf = peaks["tensor_tflops_sustained"]   # kernel timed inside a long step -> sustained figure
+        is_tc = dom != "ffma"
+        # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), if any
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(name, {}).get(dom)
+            except Exception:
+                traffic = None
+        # all tensor-core kernels together (they share the roofline): algorithmic FLOPs / their summed time
+        tc_ms = sum(v["ms"] for k, v in by_kernel.items() if k != "ffma")
+        tc_fl = sum(v["flops"] for k, v in by_kernel.items() if k != "ffma")
         roofline = {
-            "bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 split-fp16 x3)" if dom == "tcgen05" else "conv_ffma_kernel",
+            "bound": "tensor", "kernel": kernel_names.get(dom, dom),
             "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-            "peak_source": f"{peaks['source']} bf16 dense GEMM, sustained (MEASURED_PEAKS.json)",
-            "passes": 3 if dom == "tcgen05" else 1,
-            "executed_mma_frac": (3 * achieved_tf / peak_tf) if dom == "tcgen05" else None,
+            "peak_source": f"{peaks['source']} dense bf16/fp16 GEMM, sustained (MEASURED_PEAKS.json bf16_tflops_sustained)",
+            "flops_basis": "algorithmic 2*Cin*Cout*k per output sample (SURVEY 8a); executed UMMA FLOPs are 3x (split-fp16)",
+            "passes": 3 if is_tc else 1,
+            "executed_mma_frac": (3 * achieved_tf / peak_tf) if is_tc else None,
             "share_of_step": d["ms"] / total_ms, "launches_per_step": d["launches"],
-            "avg_launch_ms": d["ms"] / d["launches"], "traffic": None,
+            "avg_launch_ms": d["ms"] / d["launches"], "traffic": traffic,
+            "all_tensor_core_kernels": {"tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
+                                        "frac": (tc_fl / (tc_ms * 1e-3) / 1e12 / peak_tf) if tc_ms else None,
+                                        "share_of_step": tc_ms / total_ms},
+            "hbm_peak_gbs": peaks["hbm_gbs"],
             "by_kernel": {k: {"ms": v["ms"], "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
                               "gbs_if_unfused": v["bytes"] / (v["ms"] * 1e-3) / 1e9, "launches": v["launches"]}
                           for k, v in by_kernel.items()},

@@ -618,7 +618,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform -> uniform-register code
   const int nt = blockIdx.y;
   const int M = p.m_tiles * 128;
   const uint8_t* wsrc = p.wimg + (size_t)nt * p.kblocks * kblock_bytes;
@@ -709,15 +710,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     // ------------------------------------------------------------------ weight producer + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;                 // 0..3
     const bool is_producer = (wid == TC2_ISSUE_WARPS - 1);
-    if (lane == 0) {
+    const bool L0 = (lane == 0);   // the whole warp walks the loops (uniform control flow), lane 0 issues
+    {
       const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
       if (is_producer) {
         if (p.w_resident) {
           const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
-          mbar_expect_tx(BAR(8), total);
+          if (L0) mbar_expect_tx(BAR(8), total);
           for (uint32_t off = 0; off < total; off += 32768) {
             const uint32_t n = min(32768u, total - off);
-            bulk_g2s(smem_u32(Wbuf + off), wsrc + off, n, BAR(8));
+            if (L0) bulk_g2s(smem_u32(Wbuf + off), wsrc + off, n, BAR(8));
           }
         } else {
           int g = 0;
@@ -728,9 +730,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               const int kb0 = wi * p.kb_per_stage;
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
-              mbar_expect_tx(BAR(8 + slot), bytes);
-              bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
-                       BAR(8 + slot));
+              if (L0) {
+                mbar_expect_tx(BAR(8 + slot), bytes);
+                bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
+                         BAR(8 + slot));
+              }
             }
           }
         }
@@ -766,14 +770,18 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
             uint32_t d = acc;
             if (p.dual) {
               for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
-                umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+                if (L0) {
+                  umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+                  umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+                }
               }
             } else {
               for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                umma_f16(d, ad_hi, bd_hi, p.idesc, first);
-                umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-                umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+                if (L0) {
+                  umma_f16(d, ad_hi, bd_hi, p.idesc, first);
+                  umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+                  umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+                }
               }
             }
             if (++ks == p.ksteps) { ks = 0; ++j; }
@@ -789,11 +797,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               for (int qk = 0; qk < nkb; ++qk)
                 do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-              umma_commit(BAR(16 + slot));
+              if (L0) umma_commit(BAR(16 + slot));
             }
           }
-          umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
-          umma_commit(BAR(4 + as));   // my accumulators of this tile are complete
+          if (L0) {
+            umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
+            umma_commit(BAR(4 + as));   // my accumulators of this tile are complete
+          }
         }
       }
     }
@@ -994,7 +1004,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
 
   if (tid == 0) {
@@ -1068,8 +1079,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weights (once) + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;
-    if (lane == 0) {
-      if (wid == TC2_ISSUE_WARPS - 1) {
+    const bool L0 = (lane == 0);
+    {
+      if (wid == TC2_ISSUE_WARPS - 1 && L0) {
         mbar_expect_tx(BAR(14), 2 * w_bytes);
         for (uint32_t off = 0; off < w_bytes; off += 32768) {
           const uint32_t n = min(32768u, w_bytes - off);
@@ -1099,8 +1111,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             uint64_t ad_hi = ad_mine + a_off16;
             uint32_t d = acc + (uint32_t)wid * mt_cols;
             for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-              umma_f16(d, ad_hi, bd_hi, p.idesc2, first);
-              umma_f16(d, ad_hi + a_lo_delta16, bd_hi, p.idesc, 1u);
+              if (L0) {
+                umma_f16(d, ad_hi, bd_hi, p.idesc2, first);
+                umma_f16(d, ad_hi + a_lo_delta16, bd_hi, p.idesc, 1u);
+              }
             }
             if (++ks == p.ksteps) { ks = 0; ++j; }
           }
@@ -1114,8 +1128,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           tc_fence_after();
           run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w1s, p.dil,
                    tmem_base + (uint32_t)(as * p.acc_cols));
-          umma_commit(BAR(2 + s));
-          umma_commit(BAR(4 + as));
+          if (L0) {
+            umma_commit(BAR(2 + s));
+            umma_commit(BAR(4 + as));
+          }
         };
         auto conv2 = [&](int i) {
           const int bs = i & 1;   // acc2 is double buffered: epiB(i-1) overlaps conv2(i)
@@ -1124,8 +1140,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           tc_fence_after();
           run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1,
                    acc2_base + (uint32_t)(bs * p.acc_cols));
-          umma_commit(BAR(9));
-          umma_commit(BAR(10 + bs));
+          if (L0) {
+            umma_commit(BAR(9));
+            umma_commit(BAR(10 + bs));
+          }
         };
         if (n_my > 0) conv1(0);
         for (int i = 0; i < n_my; ++i) {
@@ -1151,11 +1169,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         if (it >= 1) mbar_wait(BAR(9), (uint32_t)((it - 1) & 1), 870);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
-        for (int mt = 0; mt < p.m_tiles; ++mt) {
-          const int r = mt * 128 + q * 32 + lane;
-          const int gpos = t0 - p2 + r;
-          const bool inside = gpos >= 0 && gpos < p.L;
-          for (int c = 0; c < nchunks; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
+          float b1v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) b1v[i] = p.bias1 ? __ldg(p.bias1 + c * 16 + i) : 0.f;
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const int r = mt * 128 + q * 32 + lane;
+            const int gpos = t0 - p2 + r;
+            const bool inside = gpos >= 0 && gpos < p.L;
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
             tmem_ld16(tcol, rr);
@@ -1163,9 +1184,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             uint32_t hp[8], lp[8];
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-              float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]);
-              float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]);
-              if (p.bias1) { v0 += __ldg(p.bias1 + c * 16 + i); v1 += __ldg(p.bias1 + c * 16 + i + 1); }
+              float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]) + b1v[i];
+              float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]) + b1v[i + 1];
               v0 = inside ? pre_act(v0, p.slope) : 0.f;
               v1 = inside ? pre_act(v1, p.slope) : 0.f;
               split_f16x2(v0, v1, hp[i >> 1], lp[i >> 1]);
