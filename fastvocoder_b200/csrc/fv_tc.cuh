@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "fv_kernels.cuh"
@@ -488,6 +489,35 @@ inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) 
 }
 
 
+// ---- thread-block-cluster helpers (weight-stream multicast) ------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> the same smem offset in every CTA of `mask`; each destination CTA's mbarrier (same offset) gets complete_tx
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // =================================================================================================
 // v2: persistent, warp-specialised pipeline
 //   warps 0-7   loaders   : global fp32 -> act/pad -> fp16 hi/lo -> A[stage]          (a_full / a_empty)
@@ -623,6 +653,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   const int nt = blockIdx.y;
   const int M = p.m_tiles * 128;
   const uint8_t* wsrc = p.wimg + (size_t)nt * p.kblocks * kblock_bytes;
+  // Weight-ring multicast: the CTAs of a cluster (launched as pairs for ring-mode layers) walk the same number of
+  // ring iterations; each fetches 1/cs of every stage and multicasts it to all of them.
+  const uint32_t cs = cluster_nctarank(), cr = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int cl_base = (int)blockIdx.x - (int)cr;                      // lowest blockIdx.x of my cluster
+  const int ring_tiles = (p.total_tiles > cl_base) ? (p.total_tiles - cl_base + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -633,13 +669,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(BAR(8 + s), 1);                // w_full: expect_tx by the producer
-      mbar_init(BAR(16 + s), p.n_issuers);     // w_empty: one tcgen05.commit per issuer
+      mbar_init(BAR(16 + s), p.n_issuers * cs);     // w_empty: one tcgen05.commit per issuer of every CTA in the cluster
     }
     fence_mbar_init();
   }
   if (warp == TC2_LOADER_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // peers' barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -723,7 +760,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
           }
         } else {
           int g = 0;
-          for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          for (int rt = 0; rt < ring_tiles; ++rt) {
             for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
               const int slot = g % p.w_stages;
               if (g >= p.w_stages) mbar_wait(BAR(16 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 500 + slot);
@@ -731,9 +768,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
               if (L0) {
-                mbar_expect_tx(BAR(8 + slot), bytes);
-                bulk_g2s(smem_u32(Wbuf + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes,
-                         BAR(8 + slot));
+                mbar_expect_tx(BAR(8 + slot), bytes);   // the full stage lands here: my slice + the peers' slices
+                const uint32_t dst = smem_u32(Wbuf + (size_t)slot * p.stage_bytes);
+                const uint8_t* src = wsrc + (size_t)kb0 * kblock_bytes;
+                if (cs == 1) {
+                  bulk_g2s(dst, src, bytes, BAR(8 + slot));
+                } else {
+                  const uint32_t slice = bytes / cs;     // k-block bytes are a multiple of 1024
+                  bulk_g2s_mcast(dst + cr * slice, src + (size_t)cr * slice, slice, BAR(8 + slot), cmask);
+                }
               }
             }
           }
@@ -797,12 +840,28 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               for (int qk = 0; qk < nkb; ++qk)
                 do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-              if (L0) umma_commit(BAR(16 + slot));
+              if (L0) {
+                if (cs == 1) umma_commit(BAR(16 + slot));
+                else umma_commit_mcast(BAR(16 + slot), cmask);   // releases the slot in every CTA of the cluster
+              }
             }
           }
           if (L0) {
             umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
             umma_commit(BAR(4 + as));   // my accumulators of this tile are complete
+          }
+        }
+        // a cluster peer may have one more tile than I do: keep consuming / releasing the shared weight ring
+        if (!p.w_resident) {
+          for (int rt = it; rt < ring_tiles; ++rt) {
+            for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
+              const int slot = g % p.w_stages;
+              mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 640 + slot);
+              if (L0) {
+                if (cs == 1) umma_commit(BAR(16 + slot));
+                else umma_commit_mcast(BAR(16 + slot), cmask);
+              }
+            }
           }
         }
       }
@@ -829,6 +888,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();   // no CTA may exit while a peer can still multicast into it
   if (warp == TC2_LOADER_WARPS) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
@@ -946,11 +1006,27 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   int gx = num_sms[dev] / L.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
-  dim3 grid(gx, L.n_tiles, 1);
-  conv_tc2_kernel<<<grid, TC2_THREADS, smem, st>>>(p);
+  static const bool no_cluster = getenv("FV_NO_CLUSTER") != nullptr;
+  const int cs = (!p.w_resident && !no_cluster && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
+  if (cs == 2) gx = (gx + 1) & ~1;   // pairs; an odd tile count leaves one CTA with ring duty only
+  if (cs == 2 && gx > num_sms[dev] / L.n_tiles) gx -= 2;
+  if (gx < cs) gx = cs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(gx, L.n_tiles, 1);
+  cfg.blockDim = dim3(TC2_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, p);
   g_launches++;
   g_tc_launches++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -1;
 }
 
 
