@@ -1006,8 +1006,9 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   int gx = num_sms[dev] / L.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
-  static const bool no_cluster = getenv("FV_NO_CLUSTER") != nullptr;
-  const int cs = (!p.w_resident && !no_cluster && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
+  // EXPERIMENTAL (round 1): the multicast ring produces wrong results on hardware, so it is opt-in until debugged.
+  static const bool use_cluster = getenv("FV_CLUSTER") != nullptr;
+  const int cs = (!p.w_resident && use_cluster && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
   if (cs == 2) gx = (gx + 1) & ~1;   // pairs; an odd tile count leaves one CTA with ring duty only
   if (cs == 2 && gx > num_sms[dev] / L.n_tiles) gx -= 2;
   if (gx < cs) gx = cs;
