@@ -511,6 +511,12 @@ __device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, ui
       "l"(src), "r"(bytes), "r"(bar), "h"(mask)
       : "memory");
 }
+// arrive on the mbarrier at the same smem offset in CTA `rank` of the cluster (plain remote arrive, release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
 // tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -644,9 +650,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * kblock_bytes : (size_t)p.w_stages * p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Wbuf + w_bytes);
   // barrier map: [0,2) a_full  [2,4) a_empty  [4,6) acc_full  [6,8) acc_empty  [8,16) w_full  [16,24) w_empty
+  //              [24,32) w_free (cluster mode: every CTA's issuers are done with the slot)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform -> uniform-register code
@@ -669,7 +676,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(BAR(8 + s), 1);                // w_full: expect_tx by the producer
-      mbar_init(BAR(16 + s), p.n_issuers * cs);     // w_empty: one tcgen05.commit per issuer of every CTA in the cluster
+      mbar_init(BAR(16 + s), p.n_issuers);     // w_empty: one (local) tcgen05.commit per issuer
+      mbar_init(BAR(24 + s), cs);               // w_free: one remote arrive per CTA of the cluster
     }
     fence_mbar_init();
   }
@@ -763,7 +771,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
           for (int rt = 0; rt < ring_tiles; ++rt) {
             for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
               const int slot = g % p.w_stages;
-              if (g >= p.w_stages) mbar_wait(BAR(16 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 500 + slot);
+              if (g >= p.w_stages) {
+                const uint32_t ph = (uint32_t)((g / p.w_stages - 1) & 1);
+                mbar_wait(BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
+                if (cs > 1) {                                        // ... tell every CTA, then wait for all of them
+                  if (L0) for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(BAR(24 + slot), r);
+                  mbar_wait(BAR(24 + slot), ph, 520 + slot);
+                }
+              }
               const int kb0 = wi * p.kb_per_stage;
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
@@ -840,10 +855,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
               for (int qk = 0; qk < nkb; ++qk)
                 do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-              if (L0) {
-                if (cs == 1) umma_commit(BAR(16 + slot));
-                else umma_commit_mcast(BAR(16 + slot), cmask);   // releases the slot in every CTA of the cluster
-              }
+              if (L0) umma_commit(BAR(16 + slot));   // local; the producers exchange "slot free" across the cluster
             }
           }
           if (L0) {
@@ -857,10 +869,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
             for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
               const int slot = g % p.w_stages;
               mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 640 + slot);
-              if (L0) {
-                if (cs == 1) umma_commit(BAR(16 + slot));
-                else umma_commit_mcast(BAR(16 + slot), cmask);
-              }
+              if (L0) umma_commit(BAR(16 + slot));
             }
           }
         }
@@ -895,7 +904,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 inline size_t tc2_smem_bytes(const Tc2Args& p) {
   const size_t a_bytes = (size_t)p.rows * p.a.Cin * 2;
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * p.NT * 64 : (size_t)p.w_stages * p.stage_bytes;
-  return p.a_stages * 2 * a_bytes + w_bytes + 25 * 8;
+  return p.a_stages * 2 * a_bytes + w_bytes + 33 * 8;
 }
 
 // Choose tile shape / buffering for one layer launch.  Preference order: weights resident in smem (no L2
