@@ -214,6 +214,68 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvArgs a) {
   }
 }
 
+// Vectorised variant (dilation 1, zero padding, K <= 8): each thread produces 4 consecutive positions from three
+// aligned float4 loads per input channel (12-sample window) instead of 4*K scalar loads.
+template <int NOUT>
+__global__ void __launch_bounds__(256) conv_narrow_v4_kernel(const ConvArgs a) {
+  extern __shared__ float smem[];   // [Cin][K][NOUT]
+  const int wn = a.Cin * a.K * NOUT;
+  for (int i = threadIdx.x; i < wn; i += blockDim.x) {
+    const int n = i % NOUT, r = i / NOUT;
+    smem[i] = n < a.N ? __ldg(a.w + (long long)r * a.N + n) : 0.f;
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* xb = a.x + (long long)b * a.x_bs;
+  float* yb = a.y + (long long)b * a.y_bs;
+  const int off = 4 - a.pad_left;   // window index of tap 0 for output 0
+  const int nquads = a.Lpos >> 2;
+  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < nquads; qd += gridDim.x * blockDim.x) {
+    const int t0 = qd << 2;
+    float acc[NOUT][4];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[n][q] = 0.f;
+    const bool okL = t0 - 4 >= 0, okR = t0 + 4 < a.Lin;
+    for (int ci = 0; ci < a.Cin; ++ci) {
+      const float4* xr = reinterpret_cast<const float4*>(xb + (long long)ci * a.Lin + t0);
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v0 = okL ? __ldg(xr - 1) : z, v1 = __ldg(xr), v2 = okR ? __ldg(xr + 1) : z;
+      float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int i = 0; i < 12; ++i) w[i] = pre_act(w[i], a.pre_slope);
+      const float* wr = smem + ci * a.K * NOUT;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j >= a.K) break;
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          const float wt = wr[j * NOUT + n];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[n][q] = fmaf(wt, w[q + j + off], acc[n][q]);   // off is 0..4: see launcher
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      if (n >= a.N) break;
+      const float bv = a.bias ? __ldg(a.bias + n) : 0.f;
+      float4 o;
+      o.x = acc[n][0] + bv; o.y = acc[n][1] + bv; o.z = acc[n][2] + bv; o.w = acc[n][3] + bv;
+      if (a.post_tanh) { o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w); }
+      *reinterpret_cast<float4*>(yb + (long long)n * a.Lpos + t0) = o;
+    }
+  }
+}
+
+inline bool conv_narrow_v4_ok(const ConvArgs& a) {
+  // window index q + j + off must stay in [0, 12): off = 4 - pad_left in [0,4], 3 + (K-1) + off <= 11
+  return a.dil == 1 && a.pad_mode == PAD_ZERO && a.K <= 8 && a.pad_left <= 4 && (a.K - 1) + (4 - a.pad_left) <= 8 &&
+         a.Lin % 4 == 0 && a.Lpos == a.Lin && a.x_bs % 4 == 0 && a.y_bs % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
+}
+
 inline bool conv_narrow_ok(const ConvArgs& a) {
   return a.N <= 4 && a.K <= 16 && a.out_layout == OUT_BCL && a.res == nullptr && a.acc_mode == ACC_STORE &&
          (size_t)a.Cin * a.K * 4 * sizeof(float) <= 40 * 1024;
@@ -223,7 +285,14 @@ inline cudaError_t launch_conv_narrow(const ConvArgs& a, cudaStream_t st) {
   long long gx = (a.Lpos + 255) / 256;
   if (gx > 148 * 32) gx = 148 * 32;
   dim3 grid((unsigned)gx, a.B);
-  if (a.N == 1) conv_narrow_kernel<1><<<grid, 256, (size_t)a.Cin * a.K * 1 * sizeof(float), st>>>(a);
+  if (conv_narrow_v4_ok(a)) {
+    long long g4 = (a.Lpos / 4 + 255) / 256;
+    if (g4 > 148 * 32) g4 = 148 * 32;
+    if (g4 < 1) g4 = 1;
+    dim3 grid4((unsigned)g4, a.B);
+    if (a.N == 1) conv_narrow_v4_kernel<1><<<grid4, 256, (size_t)a.Cin * a.K * 1 * sizeof(float), st>>>(a);
+    else conv_narrow_v4_kernel<4><<<grid4, 256, (size_t)a.Cin * a.K * 4 * sizeof(float), st>>>(a);
+  } else if (a.N == 1) conv_narrow_kernel<1><<<grid, 256, (size_t)a.Cin * a.K * 1 * sizeof(float), st>>>(a);
   else conv_narrow_kernel<4><<<grid, 256, (size_t)a.Cin * a.K * 4 * sizeof(float), st>>>(a);
   g_launches++;
   return cudaGetLastError();

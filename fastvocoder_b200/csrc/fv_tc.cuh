@@ -77,11 +77,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ int g_wait_hint = 1;   // 1: try_wait with a suspend-time hint, 0: plain try_wait polling (FV_WAIT_HINT=0)
 // Bounded wait: a broken pipeline traps (launch failure reported to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait_spin(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  const bool hint = g_wait_hint != 0;
+  while (!(hint ? mbar_try_wait(bar, parity) : mbar_try_wait_spin(bar, parity))) {
     if (clock64() - t0 > 400000000LL) {
       printf("fv_tc: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
@@ -992,7 +1005,19 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   return true;
 }
 
+inline void tc_apply_env_once() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("FV_WAIT_HINT");
+  if (e) {
+    int v = atoi(e);
+    cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(int));
+  }
+}
+
 inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
+  tc_apply_env_once();
   static int num_sms[64] = {};
   static bool attr_set[64] = {};
   int dev = 0;
@@ -1321,6 +1346,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             float xv[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(xb + o0 + (long long)i * p.L) : 0.f;
+            if (p.acc_mode != ACC_STORE) {   // running MRF sum: fold it into the prefetched addend (x + xs)
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xv[i] += ok ? yb[o0 + (long long)i * p.L] : 0.f;
+            }
             if (!waited) {
               mbar_wait(BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
               tc_fence_after();
@@ -1335,17 +1364,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               v[i] = (__uint_as_float(rr[i]) + __uint_as_float(r2[i]) + bias[i]) + xv[i];
-            if (p.acc_mode != ACC_STORE) {
-              float yv[16];
+            if (p.acc_mode == ACC_ADD_DIV) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) yv[i] = yb[o0 + (long long)i * p.L];
-              if (p.acc_mode == ACC_ADD) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = yv[i] + v[i];
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = (yv[i] + v[i]) * inv;
-              }
+              for (int i = 0; i < 16; ++i) v[i] *= inv;
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) yb[o0 + (long long)i * p.L] = v[i];
@@ -1419,6 +1440,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
                              const TcLayer& l2, int B, int C, int L, int K, int dil, float slope, int acc_mode,
                              float acc_div, cudaStream_t st) {
   if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
+  tc_apply_env_once();
   Tc3Args p{};
   if (!tc3_plan(B, C, L, K, dil, p)) return 1;
   p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2;
