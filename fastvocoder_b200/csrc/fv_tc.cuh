@@ -560,6 +560,7 @@ struct Tc2Args {
   int a_stages, acc_stages, w_resident, kb_per_stage, w_stages, stage_bytes;
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
+  int ck, nck;       // K-chunking: an A stage holds `ck` input channels of the tile; nck = Cin / ck stages per tile
   int n_issuers;     // UMMA issuer warps in use (1..4; at most 3 when the weight ring needs warp 11)
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
   uint32_t idesc;    // M=128, N=NT
@@ -656,8 +657,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   uint8_t* const smem = tc_smem;
   const ConvArgs& a = p.a;
   const int rows = p.rows;
-  const uint32_t a_bytes = (uint32_t)rows * a.Cin * 2;  // hi or lo of one A stage
+  const uint32_t a_bytes = (uint32_t)rows * p.ck * 2;   // hi or lo of one A stage (one channel chunk of the tile)
   const int kblock_bytes = p.NT * 64;
+  const int kpc = p.ck >> 4;                              // 16-channel k-steps per chunk
+  const int runs_per_grp = (kpc + p.kb_per_stage - 1) / p.kb_per_stage;   // ring stages per (chunk, tap)
   uint8_t* Abuf = smem;                                   // [a_stages][hi|lo][a_bytes]
   uint8_t* Wbuf = smem + (size_t)p.a_stages * 2 * a_bytes;
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * kblock_bytes : (size_t)p.w_stages * p.stage_bytes;
@@ -703,51 +706,53 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 
   if (warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders
-    const int nkc = a.Cin >> 3;
+    const int nkc = p.ck >> 3;                  // 8-channel groups per chunk
     const int nrb = (rows + 127) >> 7;          // row blocks of 128 (4 rows per lane)
     const int npairs = nkc * nrb;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int s = it % p.a_stages;
-      if (it >= p.a_stages) mbar_wait(BAR(2 + s), (uint32_t)((it / p.a_stages - 1) & 1), 400 + s);
+    int u = 0;                                  // A-stage unit counter: (tile, channel chunk)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
-      uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
-      uint8_t* A_lo = A_hi + a_bytes;
-      for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
-        const int kc = pr / nrb, rbk = pr - kc * nrb;
-        const float* __restrict__ xc = xb + (long long)(kc * 8) * a.Lin;
-        float v[4][8];
-        int rrow[4];
+      for (int ch = 0; ch < p.nck; ++ch, ++u) {
+        const int s = u % p.a_stages;
+        if (u >= p.a_stages) mbar_wait(BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
+        uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
+        uint8_t* A_lo = A_hi + a_bytes;
+        for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
+          const int kc = pr / nrb, rbk = pr - kc * nrb;
+          const float* __restrict__ xc = xb + (long long)(ch * p.ck + kc * 8) * a.Lin;
+          float v[4][8];
+          int rrow[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int r = rbk * 128 + t * 32 + lane;
-          rrow[t] = r;
-          int g = t0 - a.pad_left + r;
-          if (a.pad_mode == PAD_REFLECT) {
-            if (g < 0) g = -g;
-            if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+          for (int t = 0; t < 4; ++t) {
+            const int r = rbk * 128 + t * 32 + lane;
+            rrow[t] = r;
+            int g = t0 - a.pad_left + r;
+            if (a.pad_mode == PAD_REFLECT) {
+              if (g < 0) g = -g;
+              if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+            }
+            const bool ok = r < rows && g >= 0 && g < a.Lin;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * a.Lin + g) : 0.f;
           }
-          const bool ok = r < rows && g >= 0 && g < a.Lin;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * a.Lin + g) : 0.f;
+          for (int t = 0; t < 4; ++t) {
+            if (rrow[t] >= rows) continue;
+            uint32_t hp[4], lp[4];
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], a.pre_slope), pre_act(v[t][c + 1], a.pre_slope),
+                                                       hp[c >> 1], lp[c >> 1]);
+            const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
+            *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
         }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if (rrow[t] >= rows) continue;
-          uint32_t hp[4], lp[4];
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], a.pre_slope), pre_act(v[t][c + 1], a.pre_slope),
-                                                     hp[c >> 1], lp[c >> 1]);
-          const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
-          *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(0 + s));
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(0 + s));
       // The epilogue of this tile (one or two tiles from now) reads the residual and, for the MRF sum, the running
       // output.  Its 4 warps cannot keep enough DRAM requests in flight, so the loaders pull those lines into L2 now.
       if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) {
@@ -770,7 +775,6 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     const bool is_producer = (wid == TC2_ISSUE_WARPS - 1);
     const bool L0 = (lane == 0);   // the whole warp walks the loops (uniform control flow), lane 0 issues
     {
-      const int iters_per_tile = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
       if (is_producer) {
         if (p.w_resident) {
           const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
@@ -782,31 +786,33 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         } else {
           int g = 0;
           for (int rt = 0; rt < ring_tiles; ++rt) {
-            for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
-              const int slot = g % p.w_stages;
-              if (g >= p.w_stages) {
-                const uint32_t ph = (uint32_t)((g / p.w_stages - 1) & 1);
-                mbar_wait(BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
-                if (cs > 1) {                                        // ... tell every CTA, then wait for all of them
-                  if (L0) for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(BAR(24 + slot), r);
-                  mbar_wait(BAR(24 + slot), ph, 520 + slot);
+            for (int ch = 0; ch < p.nck; ++ch)
+              for (int j = 0; j < a.K; ++j)
+                for (int run = 0; run < runs_per_grp; ++run, ++g) {   // k-blocks (tap j, k-steps of chunk ch) are contiguous
+                  const int slot = g % p.w_stages;
+                  if (g >= p.w_stages) {
+                    const uint32_t ph = (uint32_t)((g / p.w_stages - 1) & 1);
+                    mbar_wait(BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
+                    if (cs > 1) {                                        // ... tell every CTA, then wait for all of them
+                      if (L0) for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(BAR(24 + slot), r);
+                      mbar_wait(BAR(24 + slot), ph, 520 + slot);
+                    }
+                  }
+                  const int kb0 = j * p.ksteps + ch * kpc + run * p.kb_per_stage;
+                  const int nkb = min(p.kb_per_stage, kpc - run * p.kb_per_stage);
+                  const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
+                  if (L0) {
+                    mbar_expect_tx(BAR(8 + slot), bytes);   // the full stage lands here: my slice + the peers' slices
+                    const uint32_t dst = smem_u32(Wbuf + (size_t)slot * p.stage_bytes);
+                    const uint8_t* src = wsrc + (size_t)kb0 * kblock_bytes;
+                    if (cs == 1) {
+                      bulk_g2s(dst, src, bytes, BAR(8 + slot));
+                    } else {
+                      const uint32_t slice = bytes / cs;     // k-block bytes are a multiple of 1024
+                      bulk_g2s_mcast(dst + cr * slice, src + (size_t)cr * slice, slice, BAR(8 + slot), cmask);
+                    }
+                  }
                 }
-              }
-              const int kb0 = wi * p.kb_per_stage;
-              const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-              const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
-              if (L0) {
-                mbar_expect_tx(BAR(8 + slot), bytes);   // the full stage lands here: my slice + the peers' slices
-                const uint32_t dst = smem_u32(Wbuf + (size_t)slot * p.stage_bytes);
-                const uint8_t* src = wsrc + (size_t)kb0 * kblock_bytes;
-                if (cs == 1) {
-                  bulk_g2s(dst, src, bytes, BAR(8 + slot));
-                } else {
-                  const uint32_t slice = bytes / cs;     // k-block bytes are a multiple of 1024
-                  bulk_g2s_mcast(dst + cr * slice, src + (size_t)cr * slice, slice, BAR(8 + slot), cmask);
-                }
-              }
-            }
           }
         }
       }
@@ -822,62 +828,66 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         const uint32_t a_lo_delta = a_bytes >> 4;
         const uint32_t mt_step16 = 128u * (uint32_t)p.n_issuers;          // A rows between my consecutive M tiles
         const uint32_t d_step = acc_mt_cols * (uint32_t)p.n_issuers;
-        int it = 0, g = 0;
+        int it = 0, g = 0, u = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-          const int s = it % p.a_stages, as = it % p.acc_stages;
-          mbar_wait(BAR(0 + s), (uint32_t)((it / p.a_stages) & 1), 610 + s);
+          const int as = it % p.acc_stages;
           if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
-          tc_fence_after();
-          const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
-          const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi0 >> 4) + (uint64_t)(wid * 128);
           const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols) + (uint32_t)wid * acc_mt_cols;
-          int j = 0, ks = 0;   // tap / k-step of the running k-block index (k-blocks are visited in order)
-          auto do_kblock = [&](int kb, uint32_t bsm) {
-            const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
-            const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
-            const uint32_t a_off16 = (uint32_t)(2 * ks) * (uint32_t)rows + (uint32_t)(j * a.dil);   // 16-B units
-            const uint32_t first = kb > 0 ? 1u : 0u;
-            uint64_t ad_hi = ad_mine + a_off16;
-            uint32_t d = acc;
-            if (p.dual) {
-              for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                if (L0) {
-                  umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
-                  umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+          for (int ch = 0; ch < p.nck; ++ch, ++u) {
+            const int s = u % p.a_stages;
+            mbar_wait(BAR(0 + s), (uint32_t)((u / p.a_stages) & 1), 610 + s);
+            tc_fence_after();
+            const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
+            const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi0 >> 4) + (uint64_t)(wid * 128);
+            // one 16-channel k-block of tap j (k-step ksl inside this chunk) on all my M tiles
+            auto do_kblock = [&](int j, int ksl, uint32_t bsm) {
+              const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
+              const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
+              const uint32_t a_off16 = (uint32_t)(2 * ksl) * (uint32_t)rows + (uint32_t)(j * a.dil);   // 16-B units
+              const uint32_t first = (ch | j | ksl) ? 1u : 0u;                     // very first k-block of the tile overwrites
+              uint64_t ad_hi = ad_mine + a_off16;
+              uint32_t d = acc;
+              if (p.dual) {
+                for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
+                  if (L0) {
+                    umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+                    umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
+                  }
+                }
+              } else {
+                for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
+                  if (L0) {
+                    umma_f16(d, ad_hi, bd_hi, p.idesc, first);
+                    umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
+                    umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+                  }
                 }
               }
-            } else {
-              for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                if (L0) {
-                  umma_f16(d, ad_hi, bd_hi, p.idesc, first);
-                  umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-                  umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
+            };
+            for (int j = 0; j < a.K; ++j) {
+              if (p.w_resident) {
+                for (int ksl = 0; ksl < kpc; ++ksl)
+                  do_kblock(j, ksl, wbase + (uint32_t)(j * p.ksteps + ch * kpc + ksl) * kblock_bytes);
+              } else {
+                for (int run = 0; run < runs_per_grp; ++run, ++g) {
+                  const int slot = g % p.w_stages;
+                  mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
+                  tc_fence_after();
+                  const int nkb = min(p.kb_per_stage, kpc - run * p.kb_per_stage);
+                  for (int qk = 0; qk < nkb; ++qk)
+                    do_kblock(j, run * p.kb_per_stage + qk,
+                              wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
+                  if (L0) umma_commit(BAR(16 + slot));   // local; the producers exchange "slot free" across the cluster
                 }
               }
             }
-            if (++ks == p.ksteps) { ks = 0; ++j; }
-          };
-          if (p.w_resident) {
-            for (int kb = 0; kb < p.kblocks; ++kb) do_kblock(kb, wbase + (uint32_t)kb * kblock_bytes);
-          } else {
-            for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
-              const int slot = g % p.w_stages;
-              mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
-              tc_fence_after();
-              const int kb0 = wi * p.kb_per_stage;
-              const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-              for (int qk = 0; qk < nkb; ++qk)
-                do_kblock(kb0 + qk, wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-              if (L0) umma_commit(BAR(16 + slot));   // local; the producers exchange "slot free" across the cluster
-            }
+            if (L0) umma_commit(BAR(2 + s));    // this A stage may be overwritten once these UMMAs have read it
           }
-          if (L0) {
-            umma_commit(BAR(2 + s));    // A stage may be overwritten once these UMMAs have read it
-            umma_commit(BAR(4 + as));   // my accumulators of this tile are complete
-          }
+          if (L0) umma_commit(BAR(4 + as));     // my accumulators of this tile are complete
         }
         // a cluster peer may have one more tile than I do: keep consuming / releasing the shared weight ring
         if (!p.w_resident) {
+          const int iters_per_tile = p.nck * a.K * runs_per_grp;
           for (int rt = it; rt < ring_tiles; ++rt) {
             for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
               const int slot = g % p.w_stages;
@@ -915,7 +925,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 }
 
 inline size_t tc2_smem_bytes(const Tc2Args& p) {
-  const size_t a_bytes = (size_t)p.rows * p.a.Cin * 2;
+  const size_t a_bytes = (size_t)p.rows * p.ck * 2;
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * p.NT * 64 : (size_t)p.w_stages * p.stage_bytes;
   return p.a_stages * 2 * a_bytes + w_bytes + 33 * 8;
 }
@@ -931,48 +941,55 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const long long w_total = (long long)kblocks * kblock_bytes;
   const long long BUDGET = 225 * 1024;
   const int need_mt = (a.Lpos + 127) / 128;
-  int kbps = 16384 / kblock_bytes;
-  if (kbps < 1) kbps = 1;
-  if (kbps > kblocks) kbps = kblocks;
-  const int stage_bytes = kbps * kblock_bytes;
-  auto a_stage_bytes = [&](int mt) { return 2LL * (mt * 128 + halo) * a.Cin * 2; };
-  struct Cand { int mt, a_st, res, w_st; double score; };
-  Cand best{0, 0, 0, 0, -1.0};
-  // crude cycle model per CTA tile (positions/cycle is maximised):
-  //   UMMA: 3 passes, each max(math NT/2 cycles, operand fetch (4 KB A + NT*32 B) / 128 B/clk)
-  //   loader ~48 B/clk of fp32 input, weight stream ~28 B/clk from L2 (zero when resident), epilogue ~48 B/clk
   const int dualf = (NT <= 128) ? 2 : 1;
-  const double c_mma3 = dualf == 2   // cycles for the 3 logical passes of one k-block on one M tile
+  // cycles for the 3 logical passes of one k-block on one M tile: math vs operand fetch (~128 B/clk of smem)
+  const double c_mma3 = dualf == 2
       ? std::max((double)NT, (4096.0 + NT * 64.0) / 128.0) + std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0)
       : 3.0 * std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
-  for (int res = 1; res >= 0; --res) {
-    for (int a_st = 2; a_st >= 1; --a_st) {
-      for (int mt = 8; mt >= 1; --mt) {
-        if (mt * NT * dualf > 512) continue;
-        if (mt > need_mt && mt > 1) continue;
-        for (int w_st = (res ? 1 : 4); w_st >= (res ? 1 : 2); --w_st) {
-          const long long wb = res ? w_total : (long long)w_st * stage_bytes;
-          if (a_st * a_stage_bytes(mt) + wb + 256 > BUDGET) continue;
-          const bool acc2 = 2 * mt * NT * dualf <= 512;
-          const double t_mma = (double)kblocks * mt * c_mma3;
-          const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 48.0 + 900.0;
-          const double t_w = res ? 0.0 : (double)w_total / 28.0 * (w_st >= 4 ? 1.0 : 4.0 / w_st);
-          const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 48.0 + 600.0;
-          const double t_core = std::max(t_mma, t_w);
-          double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
-          t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
-          // wave quantisation of the persistent grid (tiles are uniform, so the last wave may be mostly idle)
-          const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
-          long long gx = std::max(1, num_sms / L.n_tiles);
-          if (gx > tiles) gx = tiles;
-          const long long waves = (tiles + gx - 1) / gx;
-          const double tail_eff = (double)tiles / (double)(waves * gx);
-          const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);   // short sequences waste rows
-          const double sc = useful / t_tile * tail_eff;
-          if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, sc};
+  struct Cand { int mt, a_st, res, w_st, ck, kbps; double score; };
+  Cand best{0, 0, 0, 0, 0, 0, -1.0};
+  // Cycle model per CTA tile, calibrated on B200 profiles (profiles/r01_notes.md):
+  //   loaders ~14 B/clk of fp32 input (DRAM-latency bound, 8 warps x 32 loads in flight),
+  //   weight ring: bytes in flight / ~2500-cycle bulk-copy round trip (L2 hit), capped at 40 B/clk,
+  //   epilogue ~40 B/clk of output traffic.
+  const int ck_opts[4] = {a.Cin, 128, 64, 32};
+  for (int cki = 0; cki < 4; ++cki) {
+    const int ck = ck_opts[cki];
+    if (ck > a.Cin || a.Cin % ck || ck % 16 || (cki > 0 && ck == a.Cin)) continue;
+    const int nck = a.Cin / ck, kpc = ck / 16;
+    int kbps = 16384 / kblock_bytes;
+    if (kbps < 1) kbps = 1;
+    if (kbps > kpc) kbps = kpc;
+    const int stage_bytes = kbps * kblock_bytes;
+    for (int res = 1; res >= 0; --res)
+      for (int a_st = 2; a_st >= 1; --a_st)
+        for (int mt = 8; mt >= 1; --mt) {
+          if (mt * NT * dualf > 512) continue;
+          if (mt > need_mt && mt > 1) continue;
+          if (nck > 1 && a_st < 2) continue;    // chunking only pays with double-buffered stages
+          for (int w_st = (res ? 1 : 8); w_st >= (res ? 1 : 2); --w_st) {
+            const long long wb = res ? w_total : (long long)w_st * stage_bytes;
+            const long long a_stage = 2LL * (mt * 128 + halo) * ck * 2;
+            if (a_st * a_stage + wb + 512 > BUDGET) continue;
+            const bool acc2 = 2 * mt * NT * dualf <= 512;
+            const double t_mma = (double)kblocks * mt * c_mma3;
+            const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 14.0 + 600.0 * nck;
+            const double ring_bw = std::min(40.0, (double)wb / 2500.0);
+            const double t_w = res ? 0.0 : (double)w_total / ring_bw;
+            const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 40.0 + 600.0;
+            const double t_core = std::max(t_mma, t_w);
+            double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
+            t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
+            const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
+            long long gx = std::max(1, num_sms / L.n_tiles);
+            if (gx > tiles) gx = tiles;
+            const long long waves = (tiles + gx - 1) / gx;
+            const double tail_eff = (double)tiles / (double)(waves * gx);
+            const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);
+            const double sc = useful / t_tile * tail_eff;
+            if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, ck, kbps, sc};
+          }
         }
-      }
-    }
   }
   if (best.score < 0) return false;
   p.a = a;
@@ -983,9 +1000,11 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.kblocks = kblocks;
   p.a_stages = best.a_st;
   p.w_resident = best.res;
-  p.kb_per_stage = kbps;
+  p.kb_per_stage = best.kbps;
   p.w_stages = best.w_st;
-  p.stage_bytes = stage_bytes;
+  p.stage_bytes = best.kbps * kblock_bytes;
+  p.ck = best.ck;
+  p.nck = a.Cin / best.ck;
   {  // issuers: short UMMAs (narrow N) are issue-bound -> spread M tiles over several issuer warps
     int ni = best.res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1;
     if (ni > best.mt) ni = best.mt;
