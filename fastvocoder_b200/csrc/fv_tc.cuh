@@ -42,6 +42,7 @@ struct TcLayer {
   bool eligible = false;
   int NT = 0;              // N tile (divides N, multiple of 16, <= 256)
   int n_tiles = 0;
+  int n_pad = 0;           // N rounded up to a multiple of 16 (zero weight columns beyond the layer's N)
   int64_t img_offset = 0;  // byte offset of this layer's image in TcWeights::buf
   const uint8_t* image = nullptr;
 };
@@ -357,16 +358,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs p) 
 // Weight image (bind time): fp32 derived image [Cin][Kd][N] -> fp16 hi/lo UMMA-canonical blocks
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __restrict__ img, int Cin, int Kd, int N,
-                                       int NT) {
+                                       int Npad, int NT) {
   const int ksteps = Cin / 16;
-  const long long total = (long long)Cin * Kd * N;  // one thread per weight
+  const long long total = (long long)Cin * Kd * Npad;  // one thread per (padded) weight
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N);
-    const long long q = i / N;
+    const int n = (int)(i % Npad);
+    const long long q = i / Npad;
     const int j = (int)(q % Kd);
     const int ci = (int)(q / Kd);
     __half hi, lo;
-    split_f16(wd[i], hi, lo);
+    split_f16(n < N ? wd[q * N + n] : 0.f, hi, lo);
     const int nt = n / NT, nn = n - nt * NT;
     const int ks = ci >> 4, kc2 = (ci >> 3) & 1, e = ci & 7;
     const long long kb = (long long)j * ksteps + ks;
@@ -396,14 +397,17 @@ struct TcWeights {
     for (size_t i = 0; i < ls.size(); ++i) {
       const Layer& l = ls[i];
       TcLayer& t = layers[i];
-      int nt = (l.Cin % 16 == 0) ? tc_pick_nt(l.N) : 0;
+      int npad = l.N;
+      if (l.type == L_BASIS && l.N % 16) npad = (l.N + 15) / 16 * 16;   // zero-padded output columns, never stored
+      int nt = (l.Cin % 16 == 0) ? tc_pick_nt(npad) : 0;
       if (l.type == L_CONVT && l.Cout % 16) nt = 0;  // a 16-column epilogue chunk must stay inside one phase
       if (nt == 0) continue;
       t.eligible = true;
       t.NT = nt;
-      t.n_tiles = l.N / nt;
+      t.n_tiles = npad / nt;
+      t.n_pad = npad;
       t.img_offset = total;
-      total += ((int64_t)l.Cin * l.Kd * l.N * 4 + 255) / 256 * 256;
+      total += ((int64_t)l.Cin * l.Kd * npad * 4 + 255) / 256 * 256;
     }
     if (total == 0) return 0;
     if (cudaMalloc(&buf, (size_t)total) != cudaSuccess) return -1;
@@ -411,11 +415,11 @@ struct TcWeights {
       if (!layers[i].eligible) continue;
       layers[i].image = buf + layers[i].img_offset;
       const Layer& l = ls[i];
-      const long long n = (long long)l.Cin * l.Kd * l.N;
+      const long long n = (long long)l.Cin * l.Kd * layers[i].n_pad;
       long long g = (n + 255) / 256;
       if (g > 148 * 16) g = 148 * 16;
       tc_pack_weights_kernel<<<(int)g, 256, 0, st>>>(derived + l.wd_offset, buf + layers[i].img_offset, l.Cin, l.Kd,
-                                                     l.N, layers[i].NT);
+                                                     l.N, layers[i].n_pad, layers[i].NT);
       g_launches++;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
@@ -483,7 +487,7 @@ inline bool tc_plan(const ConvArgs& a, const TcLayer& L, TcArgs& p) {
 // returns 0 = launched, 1 = shape not handled (caller uses the fp32 kernel), -1 = CUDA error
 inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
   TcArgs p{};
-  if (!L.eligible || !L.image || !tc_plan(a, L, p)) return 1;
+  if (!L.eligible || !L.image || L.n_pad != a.N || !tc_plan(a, L, p)) return 1;   // v1 has no padded-N support
   p.wimg = L.image;
   const size_t smem = 2ULL * p.rows * a.Cin * 2 + (size_t)p.stages * p.stage_bytes + (2 * TC_MAX_STAGES + 2) * 8;
   static bool attr_set[64] = {};
@@ -617,6 +621,14 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
       if (!ok) continue;
+      if (LAYOUT == OUT_BLC && nbase + 16 > a.N) {   // padded tail columns (Basis: N = 15 of 16): scalar, masked
+        for (int i = 0; i < 16 && nbase + i < a.N; ++i) {
+          float vv = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + nbase + i) : 0.f);
+          if (a.post_tanh) vv = tanhf(vv);
+          yb[o0 + i] = vv;
+        }
+        continue;
+      }
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias[i];
@@ -950,7 +962,8 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   Cand best{0, 0, 0, 0, 0, 0, -1.0};
   // Cycle model per CTA tile, calibrated on B200 profiles (profiles/r01_notes.md):
   //   loaders ~14 B/clk of fp32 input (DRAM-latency bound, 8 warps x 32 loads in flight),
-  //   weight ring: bytes in flight / ~2500-cycle bulk-copy round trip (L2 hit), capped at 40 B/clk,
+  //   weight ring: bytes in flight / ~2500-cycle bulk-copy round trip, capped at ~14 B/clk per SM (all SMs stream the
+  //   same image from L2: ~4 TB/s aggregate measured) -> ring-mode layers want the largest M per weight pass,
   //   epilogue ~40 B/clk of output traffic.
   const int ck_opts[4] = {a.Cin, 128, 64, 32};
   for (int cki = 0; cki < 4; ++cki) {
@@ -974,7 +987,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
             const bool acc2 = 2 * mt * NT * dualf <= 512;
             const double t_mma = (double)kblocks * mt * c_mma3;
             const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 14.0 + 600.0 * nck;
-            const double ring_bw = std::min(40.0, (double)wb / 2500.0);
+            const double ring_bw = std::min(14.0, (double)wb / 2500.0);   // measured: ~14 B/clk/SM when every SM streams the same image
             const double t_w = res ? 0.0 : (double)w_total / ring_bw;
             const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 40.0 + 600.0;
             const double t_core = std::max(t_mma, t_w);

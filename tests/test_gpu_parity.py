@@ -18,7 +18,7 @@ from oracle import torch_port as P
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4          # north_star: within 1e-4 max-abs of the reference
-TIGHT = 2e-5        # what the exact-fp32 and split-fp16 paths actually achieve on these fixtures
+TIGHT = 3e-5        # what the exact-fp32 and split-fp16 paths actually achieve on these fixtures (worst: MB-large, K=2816)
 TC_DISABLED = bool(os.environ.get("FV_DISABLE_TC"))   # library-wide kill switch of the tcgen05 path
 
 
@@ -447,8 +447,8 @@ def test_fused_resblock1_unit_kernel(C, K, L):
     assert err < 2e-5, err
 
 
-def test_oversized_layer_falls_back_to_exact_fp32_kernel():
-    """Cin = 512 does not fit the activation tile in shared memory: the library must run the CUDA-core kernel."""
+def test_wide_layer_runs_k_chunked_on_tensor_cores():
+    """Cin = 512: the activation tile only fits shared memory per 64-channel chunk (K-chunked mainloop)."""
     rng = np.random.default_rng(1)
     B, Cin, Cout, K, L = 1, 512, 512, 3, 64
     x = rng.standard_normal((B, Cin, L)).astype(np.float32)
@@ -459,8 +459,8 @@ def test_oversized_layer_falls_back_to_exact_fp32_kernel():
     tc0 = _lib.lib().fv_tc_launch_count()
     _lib.check(_lib.lib().fv_conv1d(_lib.ptr(dx), _lib.ptr(dw), None, None, _lib.ptr(y), B, Cin, Cout, L, K, 1, 0, -1.0,
                                     0, 1, stream()))
-    assert _lib.lib().fv_tc_launch_count() == tc0
-    assert np.abs(y.cpu().numpy() - want).max() < 1e-5
+    assert _lib.lib().fv_tc_launch_count() > tc0 or TC_DISABLED
+    assert np.abs(y.cpu().numpy() - want).max() < 5e-5
 
 
 def test_model_uses_tensor_cores_when_enabled(specs):
