@@ -986,13 +986,17 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
             if (a_st * a_stage + wb + 512 > BUDGET) continue;
             const bool acc2 = 2 * mt * NT * dualf <= 512;
             const double t_mma = (double)kblocks * mt * c_mma3;
-            const double t_load = (double)(mt * 128 + halo) * a.Cin * 4.0 / 14.0 + 600.0 * nck;
+            // loaders: each of the 8 warps handles (8 channels x 128 rows) per round; a round costs one DRAM round trip
+            const int rows_t = mt * 128 + halo;
+            const int pairs = (ck / 8) * ((rows_t + 127) / 128);
+            const double t_load = nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
             const double ring_bw = std::min(14.0, (double)wb / 2500.0);   // measured: ~14 B/clk/SM when every SM streams the same image
             const double t_w = res ? 0.0 : (double)w_total / ring_bw;
             const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 40.0 + 600.0;
             const double t_core = std::max(t_mma, t_w);
             double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
             t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
+            t_tile += 3000.0;   // measured fixed cost per tile (barrier hand-offs, pipeline bubbles)
             const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
             long long gx = std::max(1, num_sms / L.n_tiles);
             if (gx > tiles) gx = tiles;
