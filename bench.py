@@ -296,7 +296,12 @@ def main():
         tpath = os.path.join(REPO, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(name, {}).get(dom)
+                t = json.load(open(tpath)).get(name, {}).get(dom)
+                if t:   # captured at a smaller batch; DRAM traffic of these kernels is proportional to positions
+                    traffic = {"bytes_per_launch": t["bytes_per_launch"] * B / t["batch"], "unit": "B",
+                               "measured_at_batch": t["batch"], "scaled_to_batch": B, "launch": t["launch"],
+                               "algorithmic_bytes": t["algorithmic_bytes"] * B / t["batch"],
+                               "source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
             except Exception:
                 traffic = None
         # all tensor-core kernels together (they share the roofline): algorithmic FLOPs / their summed time
