@@ -398,7 +398,8 @@ struct TcWeights {
       const Layer& l = ls[i];
       TcLayer& t = layers[i];
       int npad = l.N;
-      if (l.type == L_BASIS && l.N % 16) npad = (l.N + 15) / 16 * 16;   // zero-padded output columns, never stored
+      // zero-padded output columns, never stored: Basis hop (15) and the narrow output convs (conv_post 1 / 4 channels)
+      if ((l.type == L_BASIS || (l.type == L_CONV && l.N < 16)) && l.N % 16) npad = (l.N + 15) / 16 * 16;
       int nt = (l.Cin % 16 == 0) ? tc_pick_nt(npad) : 0;
       if (l.type == L_CONVT && l.Cout % 16) nt = 0;  // a 16-column epilogue chunk must stay inside one phase
       if (nt == 0) continue;
@@ -587,7 +588,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
     int r = 0, co0 = nbase;
     if (LAYOUT == OUT_PHASE) { r = nbase / a.ph_cout; co0 = nbase - r * a.ph_cout; }
     float bias[16];
-    if (a.bias) {
+    if (a.bias && (LAYOUT == OUT_PHASE || nbase + 16 <= a.N)) {
       const float4* bp = reinterpret_cast<const float4*>(a.bias + (LAYOUT == OUT_PHASE ? co0 : nbase));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -621,11 +622,14 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
       if (!ok) continue;
-      if (LAYOUT == OUT_BLC && nbase + 16 > a.N) {   // padded tail columns (Basis: N = 15 of 16): scalar, masked
-        for (int i = 0; i < 16 && nbase + i < a.N; ++i) {
-          float vv = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + nbase + i) : 0.f);
-          if (a.post_tanh) vv = tanhf(vv);
-          yb[o0 + i] = vv;
+      if (LAYOUT != OUT_PHASE && nbase + 16 > a.N) {   // zero-padded tail columns (Basis 15 of 16, conv_post 1 / 4 of 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (nbase + i < a.N) {
+            float vv = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + nbase + i) : 0.f);
+            if (a.post_tanh) vv = tanhf(vv);
+            yb[o0 + i * ostride] = vv;
+          }
         }
         continue;
       }
