@@ -583,84 +583,87 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
   const int nchunks = p.NT >> 4;
-  const int total = nchunks * p.m_tiles;
-  const float inv = 1.0f / a.acc_div;
-
-  // output address of item (chunk c, M tile mt) for this thread's position
-  auto item_addr = [&](int item, int& c, int& nbase, int& co0, long long& o0, long long& ostride) -> bool {
-    c = item / p.m_tiles;
-    const int mt = item - c * p.m_tiles;
-    nbase = nt * p.NT + c * 16;
-    co0 = nbase;
-    const int pos = t0 + mt * 128 + q * 32 + lane;
-    bool ok = pos < a.Lpos;
-    if (LAYOUT == OUT_BCL) {
-      o0 = (long long)nbase * a.Lpos + pos; ostride = a.Lpos;
-    } else if (LAYOUT == OUT_BLC) {
-      o0 = (long long)pos * a.N + nbase; ostride = 1;
+  for (int c = 0; c < nchunks; ++c) {
+    const int nbase = nt * p.NT + c * 16;
+    int r = 0, co0 = nbase;
+    if (LAYOUT == OUT_PHASE) { r = nbase / a.ph_cout; co0 = nbase - r * a.ph_cout; }
+    float bias[16];
+    if (a.bias && (LAYOUT == OUT_PHASE || nbase + 16 <= a.N)) {
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + (LAYOUT == OUT_PHASE ? co0 : nbase));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(bp + i);
+        bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w;
+      }
     } else {
-      const int r = nbase / a.ph_cout;
-      co0 = nbase - r * a.ph_cout;
-      const int t = pos * a.ph_stride + r - a.ph_pad;
-      ok = ok && t >= 0 && t < a.ph_lout;
-      o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
-    }
-    return ok;
-  };
-  // Everything that does not depend on the accumulators — bias, residual, running MRF sum — is gathered into one
-  // addend, loaded one item ahead so the global-load latency overlaps the previous item's TMEM reads and stores.
-  auto load_add = [&](int item, float (&dst)[16]) {
-    int c, nbase, co0;
-    long long o0, ostride;
-    const bool ok = item < total && item_addr(item, c, nbase, co0, o0, ostride);
-    const int bidx = (LAYOUT == OUT_PHASE) ? co0 : nbase;
-    const int nvalid = (LAYOUT == OUT_PHASE) ? 16 : min(16, a.N - nbase);   // zero-padded tail columns have no bias / output
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      float v = 0.f;
-      if (ok && i < nvalid) {
-        if (a.bias) v = __ldg(a.bias + bidx + i);
-        if (rb) v += __ldg(rb + o0 + i * ostride);
-        if (a.acc_mode != ACC_STORE) v += yb[o0 + i * ostride];
+      for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+    }
+    for (int mt = 0; mt < p.m_tiles; ++mt) {
+      const int pos = t0 + mt * 128 + q * 32 + lane;
+      uint32_t rr[16];
+      const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
+      tmem_ld16(tcol, rr);
+      if (p.dual) {  // columns [NT, 2NT) hold the separately accumulated hi*lo terms
+        uint32_t r2[16];
+        tmem_ld16(tcol + (uint32_t)p.NT, r2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
       }
-      dst[i] = v;
-    }
-  };
-  auto process = [&](int item, const float (&add)[16]) {
-    int c, nbase, co0;
-    long long o0, ostride;
-    const bool ok = item_addr(item, c, nbase, co0, o0, ostride);
-    const int mt = item - c * p.m_tiles;
-    uint32_t rr[16];
-    const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
-    tmem_ld16(tcol, rr);
-    if (p.dual) {  // columns [NT, 2NT) hold the separately accumulated hi*lo terms
-      uint32_t r2[16];
-      tmem_ld16(tcol + (uint32_t)p.NT, r2);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
-    }
-    if (!ok) return;
-    const int nvalid = (LAYOUT == OUT_PHASE) ? 16 : min(16, a.N - nbase);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i < nvalid) {
-        float v = __uint_as_float(rr[i]) + add[i];
-        if (a.acc_mode == ACC_ADD_DIV) v *= inv;   // xs / num_kernels (hifigan.py:103) via the fp32 reciprocal (<= 1 ulp)
-        if (a.post_tanh) v = tanhf(v);
-        yb[o0 + i * ostride] = v;
+      long long o0, ostride;
+      bool ok = pos < a.Lpos;
+      if (LAYOUT == OUT_BCL) {
+        o0 = (long long)nbase * a.Lpos + pos; ostride = a.Lpos;
+      } else if (LAYOUT == OUT_BLC) {
+        o0 = (long long)pos * a.N + nbase; ostride = 1;
+      } else {
+        const int t = pos * a.ph_stride + r - a.ph_pad;
+        ok = ok && t >= 0 && t < a.ph_lout;
+        o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
-    }
-  };
-
-  float addA[16], addB[16];   // ping-pong: the addend of item k+1 is in flight while item k is processed
-  load_add(0, addA);
-  for (int item = 0; item < total; item += 2) {
-    load_add(item + 1, addB);
-    process(item, addA);
-    if (item + 1 < total) {
-      load_add(item + 2, addA);
-      process(item + 1, addB);
+      if (!ok) continue;
+      if (LAYOUT != OUT_PHASE && nbase + 16 > a.N) {   // zero-padded tail columns (Basis 15 of 16, conv_post 1 / 4 of 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (nbase + i < a.N) {
+            float vv = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + nbase + i) : 0.f);
+            if (a.post_tanh) vv = tanhf(vv);
+            yb[o0 + i * ostride] = vv;
+          }
+        }
+        continue;
+      }
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias[i];
+      if (rb) {
+        float rv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = __ldg(rb + o0 + i * ostride);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += rv[i];
+      }
+      if (a.acc_mode != ACC_STORE) {
+        float yv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) yv[i] = yb[o0 + i * ostride];
+        if (a.acc_mode == ACC_ADD) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = yv[i] + v[i];
+        } else {
+          // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division,
+          // far inside the 1e-4 budget, and ~10 instructions per element cheaper (this launch was 2x its siblings)
+          const float inv = 1.0f / a.acc_div;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (yv[i] + v[i]) * inv;
+        }
+      }
+      if (a.post_tanh) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = v[i];
     }
   }
 }
