@@ -132,6 +132,7 @@ def run_reference(args, rank, world):
         return
     name = args.model
     ypath, B, T, label = WORKLOADS[name]
+    T = args.frames or T
     cfg = load_yaml(ypath)
     from fastvocoder_b200 import build_generator
     model = build_generator(name, cfg)

@@ -59,6 +59,17 @@ struct fv_handle {
 namespace fv {
 
 // ---- weight derivation ----------------------------------------------------------------------------
+static inline float* pair_bias_ptr(const Layer& l, float* wd) {   // summed bias lives right after the image
+  return wd + ((int64_t)l.Cin * l.N + 63) / 64 * 64;
+}
+static int derive_pair(const Layer& l, const float* wa, const float* wb, const float* ba, const float* bb, float* wd,
+                       cudaStream_t st) {
+  derive_pair_kernel<<<grid_for(2LL * l.Cout * l.Cout), 256, 0, st>>>(wa, wb, ba, bb, wd, pair_bias_ptr(l, wd), l.Cout);
+  g_launches++;
+  FV_CUDA(cudaGetLastError());
+  return FV_OK;
+}
+
 static int derive_layer(const Layer& l, const float* w_canon, float* wd, cudaStream_t st) {
   const long long n = (long long)l.Cin * l.Kd * l.N;
   const int g = grid_for(n);
@@ -84,6 +95,8 @@ struct LayerCall {
   int post_tanh = 0;
   long long x_bs = -1, y_bs = -1, res_bs = -1;  // -1: dense
   bool allow_tc = true;
+  const float* x2 = nullptr;   // L_PAIR: second input (the un-activated stack input for the skip layer)
+  float pre_slope2 = -1.f;
 };
 
 static long long layer_out_len(const Layer& l, long long Lin) {
@@ -108,6 +121,18 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
     a.out_layout = OUT_BCL;
     a.bias_mod = l.Cout;
     out_per_b = (long long)l.Cout * c.Lin;
+  } else if (l.type == L_PAIR) {   // two 1x1 convs summed: channels [0,C) from x, [C,2C) from x2
+    a.Lpos = (int)c.Lin;
+    a.pad_left = 0;
+    a.out_layout = OUT_BCL;
+    a.bias_mod = l.Cout;
+    out_per_b = (long long)l.Cout * c.Lin;
+    a.x2 = c.x2;
+    a.cin_split = l.Cout;
+    a.pre_slope2 = c.pre_slope2;
+    a.x_bs = c.x_bs >= 0 ? c.x_bs : (long long)l.Cout * c.Lin;
+    a.x2_bs = (long long)l.Cout * c.Lin;
+    if (!c.x2) return fail(FV_EINVAL, "pair layer needs two inputs");
   } else if (l.type == L_CONVT) {
     const long long Lout = Model::convt_out_len(l, c.Lin);
     a.Lpos = (int)((Lout - 1 + l.padding) / l.stride + 1);
@@ -186,6 +211,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   static const bool fuse_disabled_env = getenv("FV_NO_FUSE") != nullptr;
   const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES) && !tc_disabled_env;
   const bool fuse_ok = !fuse_disabled_env;
+  const bool pair_ok = !fuse_disabled_env;   // ResidualStack: fuse the two 1x1 convs (both kernels support two inputs)
   const int Be = eff_batch(m, B, flags);
   const size_t each = max_act_floats(m, Be, T);
   const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
@@ -202,6 +228,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
 
   auto wd = [&](int li) { return h->derived + m.layers[li].wd_offset; };
   auto bias = [&](int li) -> const float* {
+    if (m.layers[li].type == L_PAIR) return pair_bias_ptr(m.layers[li], h->derived + m.layers[li].wd_offset);
     return m.layers[li].b_param >= 0 ? h->packed + m.params[m.layers[li].b_param].offset : nullptr;
   };
   auto tcl = [&](int li) -> const TcLayer* { return h->tc.layer(li); };
@@ -327,12 +354,19 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
           LayerCall l1;
           l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT;
           if ((rc = call(sk.dil_conv, l1))) return rc;
-          LayerCall ls;
-          ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout;
-          if ((rc = call(sk.skip, ls))) return rc;
-          LayerCall l2;
-          l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f;
-          if ((rc = call(sk.conv1x1, l2))) return rc;
+          if (pair_ok && sk.pair >= 0) {   // stack.4(lrelu(h)) + skip_layer(c) as one two-input 1x1 GEMM-conv
+            LayerCall lp;
+            lp.x = bufH; lp.pre_slope = 0.2f; lp.x2 = sc_in; lp.pre_slope2 = -1.f;
+            lp.y = dst; lp.B = nb; lp.Lin = Lout;
+            if ((rc = call(sk.pair, lp))) return rc;
+          } else {
+            LayerCall ls;
+            ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout;
+            if ((rc = call(sk.skip, ls))) return rc;
+            LayerCall l2;
+            l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f;
+            if ((rc = call(sk.conv1x1, l2))) return rc;
+          }
           sc_in = dst;
         }
       }
@@ -484,7 +518,13 @@ int fv_bind_weights(fv_handle* h, const float* packed_dev, int64_t n_floats, con
   h->tc.release();
   FV_CUDA(cudaMalloc(&h->derived, sizeof(float) * (size_t)h->model.derived_floats));
   for (const Layer& l : h->model.layers) {
-    int rc = derive_layer(l, packed_dev + h->model.params[l.w_param].offset, h->derived + l.wd_offset, st);
+    int rc;
+    if (l.type == L_PAIR) {
+      auto P = [&](int idx) -> const float* { return idx >= 0 ? packed_dev + h->model.params[idx].offset : nullptr; };
+      rc = derive_pair(l, P(l.w_param), P(l.w_param2), P(l.b_param), P(l.b_param2), h->derived + l.wd_offset, st);
+    } else {
+      rc = derive_layer(l, packed_dev + h->model.params[l.w_param].offset, h->derived + l.wd_offset, st);
+    }
     if (rc) return rc;
   }
   if (h->tc.build(h->model.layers, h->derived, st)) return fail(FV_ECUDA, "tensor-core weight image build failed");

@@ -32,6 +32,11 @@ struct ConvArgs {
   // OUT_PHASE (ConvTranspose1d): n = r*ph_cout + co ; t = pos*ph_stride + r - ph_pad in [0, ph_lout)
   int ph_stride, ph_pad, ph_cout, ph_lout;
   long long x_bs, y_bs, res_bs;  // batch strides in floats
+  // two-input form (L_PAIR): input channels >= cin_split come from x2 (own pre-activation); 0 = single input
+  const float* x2;
+  int cin_split;
+  float pre_slope2;
+  long long x2_bs;
 };
 
 // LeakyReLU with 0 <= slope <= 1 (slope 0 = ReLU) is max(v, slope*v); slope < 0 means "no activation".
@@ -81,7 +86,10 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
       const int ci = ci0 + warp;
       float* row = sx + warp * XW;
       const bool cok = ci < a.Cin;
-      const float* xr = xb + (long long)ci * a.Lin;
+      const bool second = a.cin_split > 0 && ci >= a.cin_split;
+      const float* xr = second ? a.x2 + (long long)b * a.x2_bs + (long long)(ci - a.cin_split) * a.Lin
+                               : xb + (long long)ci * a.Lin;
+      const float slope = second ? a.pre_slope2 : a.pre_slope;
       for (int s = lane; s < XW; s += 32) {
         int g = t0 - a.pad_left + s;
         if (a.pad_mode == PAD_REFLECT) {
@@ -89,7 +97,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
           if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
         }
         float v = 0.f;
-        if (cok && g >= 0 && g < a.Lin) v = pre_act(__ldg(xr + g), a.pre_slope);
+        if (cok && g >= 0 && g < a.Lin) v = pre_act(__ldg(xr + g), slope);
         row[s] = v;
       }
     }
@@ -277,7 +285,7 @@ inline bool conv_narrow_v4_ok(const ConvArgs& a) {
 }
 
 inline bool conv_narrow_ok(const ConvArgs& a) {
-  return a.N <= 4 && a.K <= 16 && a.out_layout == OUT_BCL && a.res == nullptr && a.acc_mode == ACC_STORE &&
+  return a.cin_split == 0 && a.N <= 4 && a.K <= 16 && a.out_layout == OUT_BCL && a.res == nullptr && a.acc_mode == ACC_STORE &&
          (size_t)a.Cin * a.K * 4 * sizeof(float) <= 40 * 1024;
 }
 
@@ -354,6 +362,18 @@ __global__ void derive_convt_kernel(const float* __restrict__ w, float* __restri
     const int kk = r + (M - 1 - mp) * stride;
     wd[i] = kk < K ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
   }
+}
+// Pair of 1x1 convs (ResidualStack stack.4 + skip_layer): [C][C][1] x2 -> [2C][1][C] and summed bias
+__global__ void derive_pair_kernel(const float* __restrict__ wa, const float* __restrict__ wb, const float* __restrict__ ba,
+                                   const float* __restrict__ bb, float* __restrict__ wd, float* __restrict__ bias, int C) {
+  const long long n = 2LL * C * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % C);
+    const int ci = (int)(i / C);
+    wd[i] = ci < C ? wa[(long long)co * C + ci] : wb[(long long)co * C + (ci - C)];
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C; i += gridDim.x * blockDim.x)
+    bias[i] = (ba ? ba[i] : 0.f) + (bb ? bb[i] : 0.f);
 }
 // Basis Linear [L][C] -> [C][2][hop]: tap 0 <-> frame n-1 second half (rows hop..L-1), tap 1 <-> frame n first half
 __global__ void derive_basis_kernel(const float* __restrict__ w, float* __restrict__ wd, int L, int C) {

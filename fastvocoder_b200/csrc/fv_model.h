@@ -28,7 +28,7 @@ struct Param {
   }
 };
 
-enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2 };
+enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2, L_PAIR = 3 };
 
 // One learned layer as the kernels see it (a stride-1 "GEMM conv" over time):
 //   y[n, pos] = bias[n % bias_mod] + sum_{ci, j} Wd[ci][j][n] * act(x)[ci, pos - pad_left + j*dil]
@@ -39,6 +39,7 @@ enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2 };
 struct Layer {
   LayerType type = L_CONV;
   int w_param = -1, b_param = -1;
+  int w_param2 = -1, b_param2 = -1;  // L_PAIR: second 1x1 conv (the skip layer) fused along the input-channel axis
   int Cin = 0, Cout = 0, K = 0, dil = 1;
   int stride = 1, padding = 0, output_padding = 0;  // ConvTranspose1d
   // derived GEMM view
@@ -56,6 +57,7 @@ struct Branch {
 };
 struct Stack {  // MelGAN ResidualStack
   int dil_conv = -1, conv1x1 = -1, skip = -1, dilation = 1;
+  int pair = -1;  // fused  W_1x1 * lrelu(h) + W_skip * c + (b_1x1 + b_skip): one two-input 1x1 GEMM-conv (Cin = 2C)
 };
 struct Stage {
   int up = -1;
@@ -224,6 +226,18 @@ struct Model {
           sk.conv1x1 = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
           snprintf(buf, sizeof buf, "melgan.%d.skip_layer", idx);
           sk.skip = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
+          {  // virtual fused layer over the two 1x1 convs (no parameters of its own)
+            Layer pl;
+            pl.type = L_PAIR;
+            pl.Cin = 2 * st.Cout; pl.Cout = st.Cout; pl.K = 1; pl.dil = 1;
+            pl.w_param = layers[sk.conv1x1].w_param; pl.b_param = layers[sk.conv1x1].b_param;
+            pl.w_param2 = layers[sk.skip].w_param; pl.b_param2 = layers[sk.skip].b_param;
+            pl.N = st.Cout; pl.Kd = 1;
+            pl.wd_offset = derived_floats;
+            derived_floats += ((int64_t)pl.Cin * pl.N + 63) / 64 * 64 + (pl.N + 63) / 64 * 64;  // image + summed bias
+            layers.push_back(pl);
+            sk.pair = (int)layers.size() - 1;
+          }
           st.stacks.push_back(sk);
           dil *= c.stack_kernel_size;
           idx += 1;

@@ -488,7 +488,7 @@ inline bool tc_plan(const ConvArgs& a, const TcLayer& L, TcArgs& p) {
 // returns 0 = launched, 1 = shape not handled (caller uses the fp32 kernel), -1 = CUDA error
 inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
   TcArgs p{};
-  if (!L.eligible || !L.image || L.n_pad != a.N || !tc_plan(a, L, p)) return 1;   // v1 has no padded-N support
+  if (!L.eligible || !L.image || L.n_pad != a.N || a.cin_split != 0 || !tc_plan(a, L, p)) return 1;   // v1: no padded N / two-input
   p.wimg = L.image;
   const size_t smem = 2ULL * p.rows * a.Cin * 2 + (size_t)p.stages * p.stage_bytes + (2 * TC_MAX_STAGES + 2) * 8;
   static bool attr_set[64] = {};
@@ -737,7 +737,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         uint8_t* A_lo = A_hi + a_bytes;
         for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
           const int kc = pr / nrb, rbk = pr - kc * nrb;
-          const float* __restrict__ xc = xb + (long long)(ch * p.ck + kc * 8) * a.Lin;
+          const int cg = ch * p.ck + kc * 8;                     // first of 8 global input channels of this group
+          const bool second = a.cin_split > 0 && cg >= a.cin_split;   // two-input (pair) layers: channels >= split come from x2
+          const float* __restrict__ xc = second ? a.x2 + (long long)b * a.x2_bs + (long long)(cg - a.cin_split) * a.Lin
+                                                : xb + (long long)cg * a.Lin;
+          const float slope = second ? a.pre_slope2 : a.pre_slope;
           float v[4][8];
           int rrow[4];
 #pragma unroll
@@ -758,7 +762,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
             if (rrow[t] >= rows) continue;
             uint32_t hp[4], lp[4];
 #pragma unroll
-            for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], a.pre_slope), pre_act(v[t][c + 1], a.pre_slope),
+            for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], slope), pre_act(v[t][c + 1], slope),
                                                        hp[c >> 1], lp[c >> 1]);
             const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
             *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
