@@ -100,7 +100,7 @@ struct LayerCall {
 };
 
 static long long layer_out_len(const Layer& l, long long Lin) {
-  if (l.type == L_CONV) return Lin;
+  if (l.type == L_CONV || l.type == L_PAIR) return Lin;
   if (l.type == L_CONVT) return Model::convt_out_len(l, Lin);
   return (Lin + 1) * l.N;  // basis: samples
 }
