@@ -12,6 +12,9 @@ if __name__ == "__main__":
     elif mode == "test":
         from fastvocoder_b200.synthesizer import run_test
         run_test()
+    elif mode == "publish":
+        from fastvocoder_b200.synthesizer import run_publisher
+        run_publisher()
     else:
-        raise SystemExit(f"MODE={mode!r}: only the inference modes (synthesize, test) exist in this repo; "
-                         "train / preprocess / publish are outside the generator forward path")
+        raise SystemExit(f"MODE={mode!r}: only the inference modes (synthesize, test, publish) exist in this repo; "
+                         "train / preprocess are outside the generator forward path")

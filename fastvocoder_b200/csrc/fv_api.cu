@@ -157,8 +157,7 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   // zero-padded-N layers (N < 16) have no residual / accumulate support in the masked epilogue
   const bool padded_ok = !tcl || tcl->n_pad == l.N || (c.res == nullptr && c.acc_mode == ACC_STORE);
   if (c.allow_tc && !tc_disabled && tcl && tcl->eligible && padded_ok) {
-    static const bool tc_v1 = getenv("FV_TC_V1") != nullptr;  // previous (non-persistent) kernel, kept for A/B runs
-    int rc = tc_v1 ? launch_conv_tc(a, *tcl, st) : launch_conv_tc2(a, *tcl, st);
+    int rc = launch_conv_tc2(a, *tcl, st);
     if (rc == 0) {
       if (used_tc) *used_tc = 1;
       return FV_OK;

@@ -12,12 +12,8 @@
 // DESIGN.md), so each operand is split x = hi + lo (both fp16, hi = rn(x), lo = rn(x - hi)) and each logical
 // product is three kind::f16 UMMAs (hi*hi + hi*lo + lo*hi) accumulated in fp32 TMEM: error ~2e-6.
 //
-// Pipeline per CTA (256 threads):
-//   all warps : global -> (pre-activation, zero/reflect padding, fp16 split) -> shared A tile
-//   warp 0/t0 : weight producer, cp.async.bulk (TMA bulk engine) of pre-packed hi/lo weight blocks into a
-//               ring of stages, mbarrier complete_tx
-//   warp 1/t0 : UMMA issuer, tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit -> stage release / epilogue go
-//   all warps : tcgen05.ld accumulators -> bias / residual / MRF accumulate / tanh -> coalesced global stores
+// Kernels in this file: conv_tc2_kernel (persistent warp-specialised GEMM-conv, K-chunked, weight ring or resident
+// weights), conv_tc3_fused_kernel (fused ResBlock1 unit).  The first, non-persistent kernel of round 1 is in git history.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -36,7 +32,6 @@ namespace fv {
 extern std::atomic<long long> g_tc_launches;
 
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 256;
 
 struct TcLayer {
   bool eligible = false;
@@ -45,15 +40,6 @@ struct TcLayer {
   int n_pad = 0;           // N rounded up to a multiple of 16 (zero weight columns beyond the layer's N)
   int64_t img_offset = 0;  // byte offset of this layer's image in TcWeights::buf
   const uint8_t* image = nullptr;
-};
-
-struct TcArgs {
-  ConvArgs a;
-  const uint8_t* wimg;  // [n_tile][kblock = j*ksteps + ks][kc2][hi|lo][NT][8] fp16
-  int NT, m_tiles, rows, ksteps, kblocks;
-  int kb_per_stage, stages, stage_bytes;
-  int tmem_cols;
-  uint32_t idesc;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -181,180 +167,6 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi2, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const TcArgs p) {
-  extern __shared__ __align__(128) uint8_t tc_smem[];
-  uint8_t* const smem = tc_smem;
-  const ConvArgs& a = p.a;
-  const int rows = p.rows;
-  const uint32_t a_bytes = (uint32_t)rows * a.Cin * 2;  // one of hi / lo
-  uint8_t* A_hi = smem;
-  uint8_t* A_lo = smem + a_bytes;
-  uint8_t* Bst = smem + 2 * a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bst + (size_t)p.stages * p.stage_bytes);
-  const uint32_t full0 = smem_u32(bars);
-  const uint32_t empty0 = smem_u32(bars + TC_MAX_STAGES);
-  const uint32_t tfull = smem_u32(bars + 2 * TC_MAX_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, nt = blockIdx.y;
-  const int t0 = blockIdx.x * (p.m_tiles * 128);
-  const int kblock_bytes = p.NT * 64;
-  const int n_stage_iters = (p.kblocks + p.kb_per_stage - 1) / p.kb_per_stage;
-  const uint8_t* wsrc = p.wimg + (size_t)nt * p.kblocks * kblock_bytes;
-
-  if (tid == 0) {
-    for (int i = 0; i < p.stages; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
-    }
-    mbar_init(tfull, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-
-  // weight producer: stage iteration it -> ring slot it % stages
-  auto produce = [&](int it) {
-    const int slot = it % p.stages;
-    if (it >= p.stages) mbar_wait(empty0 + 8 * slot, (uint32_t)((it / p.stages - 1) & 1), 100 + slot);
-    const int kb0 = it * p.kb_per_stage;
-    const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-    const uint32_t bytes = (uint32_t)nkb * kblock_bytes;
-    mbar_expect_tx(full0 + 8 * slot, bytes);
-    bulk_g2s(smem_u32(Bst + (size_t)slot * p.stage_bytes), wsrc + (size_t)kb0 * kblock_bytes, bytes, full0 + 8 * slot);
-  };
-  const int prefetch = min(p.stages, n_stage_iters);
-  if (tid == 0) {  // weights do not depend on the activation tile: start streaming them right away
-    for (int it = 0; it < prefetch; ++it) produce(it);
-  }
-
-  // ---- activation tile: global fp32 -> act -> fp16 hi/lo -> shared [kc][row][8] ------------------
-  {
-    const float* xb = a.x + (long long)b * a.x_bs;
-    const int nkc = a.Cin >> 3;
-    int kc = 0, r = tid;
-    while (r >= rows) { r -= rows; ++kc; }
-    while (kc < nkc) {
-      int g = t0 - a.pad_left + r;
-      if (a.pad_mode == PAD_REFLECT) {
-        if (g < 0) g = -g;
-        if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
-      }
-      float v[8];
-      if (g >= 0 && g < a.Lin) {
-        const float* xp = xb + (long long)(kc * 8) * a.Lin + g;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = pre_act(__ldg(xp + (long long)c * a.Lin), a.pre_slope);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[c] = 0.f;
-      }
-      __half hi[8], lo[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) split_f16(v[c], hi[c], lo[c]);
-      const uint32_t off = ((uint32_t)kc * rows + r) * 16;
-      *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
-                                                         pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-      *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                                         pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
-      r += TC_THREADS;
-      while (r >= rows) { r -= rows; ++kc; }
-    }
-  }
-  fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0)
-      for (int it = prefetch; it < n_stage_iters; ++it) produce(it);
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t a_hi0 = smem_u32(A_hi), a_lo0 = smem_u32(A_lo);
-      const uint32_t a_lbo = (uint32_t)rows * 16;  // bytes between the two 8-channel chunks of one K=16 step
-      const uint32_t b_lbo = (uint32_t)p.NT * 32;  // hi and lo rows of one 8-channel chunk are adjacent
-      for (int it = 0; it < n_stage_iters; ++it) {
-        const int slot = it % p.stages;
-        mbar_wait(full0 + 8 * slot, (uint32_t)((it / p.stages) & 1), 200 + slot);
-        tc_fence_after();
-        const int kb0 = it * p.kb_per_stage;
-        const int nkb = min(p.kb_per_stage, p.kblocks - kb0);
-        const uint32_t bs = smem_u32(Bst + (size_t)slot * p.stage_bytes);
-        for (int q = 0; q < nkb; ++q) {
-          const int kb = kb0 + q;
-          const int j = kb / p.ksteps, ks = kb - j * p.ksteps;
-          const uint64_t bd_hi = make_kmajor_desc(bs + q * kblock_bytes, b_lbo, 128);
-          const uint64_t bd_lo = make_kmajor_desc(bs + q * kblock_bytes + p.NT * 16, b_lbo, 128);
-          const uint32_t a_k = (uint32_t)(2 * ks) * a_lbo;
-          for (int mt = 0; mt < p.m_tiles; ++mt) {
-            const uint32_t a_off = a_k + (uint32_t)(mt * 128 + j * a.dil) * 16;
-            const uint64_t ad_hi = make_kmajor_desc(a_hi0 + a_off, a_lbo, 128);
-            const uint64_t ad_lo = make_kmajor_desc(a_lo0 + a_off, a_lbo, 128);
-            const uint32_t d = tmem_base + (uint32_t)(mt * p.NT);
-            umma_f16(d, ad_hi, bd_hi, p.idesc, kb > 0 ? 1u : 0u);
-            umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-            umma_f16(d, ad_lo, bd_hi, p.idesc, 1u);
-          }
-        }
-        umma_commit(empty0 + 8 * slot);  // frees the ring slot once these UMMAs have read it
-      }
-      umma_commit(tfull);  // accumulators complete
-    }
-    __syncwarp();
-  }
-
-  // ---- epilogue: TMEM -> registers -> bias / residual / accumulate / tanh -> global ---------------
-  mbar_wait(tfull, 0, 300);
-  tc_fence_after();
-  {
-    const int q = warp & 3;   // TMEM lane quarter this warp may access
-    const int cp = warp >> 2; // column-chunk parity
-    float* yb = a.y + (long long)b * a.y_bs;
-    const float* rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
-    const int nchunks = p.NT >> 4;
-    for (int mt = 0; mt < p.m_tiles; ++mt) {
-      const int pos = t0 + mt * 128 + q * 32 + lane;
-      const bool pos_ok = pos < a.Lpos;
-      for (int c = cp; c < nchunks; c += 2) {
-        uint32_t rr[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT + c * 16), rr);
-        if (!pos_ok) continue;
-        const int nbase = nt * p.NT + c * 16;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = nbase + i;
-          long long o;
-          if (a.out_layout == OUT_BCL) {
-            o = (long long)n * a.Lpos + pos;
-          } else if (a.out_layout == OUT_BLC) {
-            o = (long long)pos * a.N + n;
-          } else {
-            const int r = n / a.ph_cout, co = n - r * a.ph_cout;
-            const int t = pos * a.ph_stride + r - a.ph_pad;
-            if (t < 0 || t >= a.ph_lout) continue;
-            o = (long long)co * a.ph_lout + t;
-          }
-          float v = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + (n % a.bias_mod)) : 0.f);
-          if (rb) v += rb[o];
-          if (a.acc_mode == ACC_ADD) v = yb[o] + v;
-          else if (a.acc_mode == ACC_ADD_DIV) v = (yb[o] + v) / a.acc_div;
-          if (a.post_tanh) v = tanhf(v);
-          yb[o] = v;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Weight image (bind time): fp32 derived image [Cin][Kd][N] -> fp16 hi/lo UMMA-canonical blocks
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __restrict__ img, int Cin, int Kd, int N,
@@ -432,80 +244,6 @@ struct TcWeights {
     layers.clear();
   }
 };
-
-// Tile plan: prefer two co-resident CTAs per SM (their load / MMA / epilogue phases overlap), otherwise one big CTA.
-inline bool tc_plan(const ConvArgs& a, const TcLayer& L, TcArgs& p) {
-  const int NT = L.NT;
-  const int halo = (a.K - 1) * a.dil;
-  const int kblock_bytes = NT * 64;
-  const int ksteps = a.Cin / 16;
-  const int kblocks = a.K * ksteps;
-  int kbps = 16384 / kblock_bytes;
-  if (kbps < 1) kbps = 1;
-  if (kbps > kblocks) kbps = kblocks;
-  const int stage_bytes = kbps * kblock_bytes;
-  const int need_mt = (a.Lpos + 127) / 128;
-  auto smem_for = [&](int mt, int st) -> long long {
-    return 2LL * (mt * 128 + halo) * a.Cin * 2 + (long long)st * stage_bytes + (2 * TC_MAX_STAGES + 2) * 8;
-  };
-  int best_mt = 0, best_st = 0;
-  int mtA = 0;  // two CTAs per SM: <= 112 KB smem and <= 256 TMEM columns each
-  {
-    int cap = 256 / NT;
-    if (cap > 8) cap = 8;
-    if (cap > need_mt) cap = need_mt;
-    for (int mt = cap; mt >= 1 && !mtA; --mt)
-      if (smem_for(mt, 3) <= 112 * 1024) mtA = mt;
-  }
-  int mtB = 0, stB = 0;  // one CTA per SM
-  {
-    int cap = 512 / NT;
-    if (cap > 8) cap = 8;
-    if (cap > need_mt) cap = need_mt;
-    for (int st = 4; st >= 2 && !mtB; --st)
-      for (int mt = cap; mt >= 1 && !mtB; --mt)
-        if (smem_for(mt, st) <= 224 * 1024) { mtB = mt; stB = st; }
-  }
-  if (mtA >= 1 && 2 * mtA >= mtB) { best_mt = mtA; best_st = 3; }
-  else { best_mt = mtB; best_st = stB; }
-  if (!best_mt) return false;
-  p.a = a;
-  p.NT = NT;
-  p.m_tiles = best_mt;
-  p.rows = best_mt * 128 + halo;
-  p.ksteps = ksteps;
-  p.kblocks = kblocks;
-  p.kb_per_stage = kbps;
-  p.stages = best_st;
-  p.stage_bytes = stage_bytes;
-  int cols = 32;
-  while (cols < best_mt * NT) cols <<= 1;
-  p.tmem_cols = cols;
-  p.idesc = make_idesc_f16(128, NT);
-  return true;
-}
-
-// returns 0 = launched, 1 = shape not handled (caller uses the fp32 kernel), -1 = CUDA error
-inline int launch_conv_tc(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
-  TcArgs p{};
-  if (!L.eligible || !L.image || L.n_pad != a.N || a.cin_split != 0 || !tc_plan(a, L, p)) return 1;   // v1: no padded N / two-input
-  p.wimg = L.image;
-  const size_t smem = 2ULL * p.rows * a.Cin * 2 + (size_t)p.stages * p.stage_bytes + (2 * TC_MAX_STAGES + 2) * 8;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return -1;
-    attr_set[dev & 63] = true;
-  }
-  dim3 grid((a.Lpos + p.m_tiles * 128 - 1) / (p.m_tiles * 128), L.n_tiles, a.B);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
-  g_launches++;
-  g_tc_launches++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
 
 // ---- thread-block-cluster helpers (weight-stream multicast) ------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {

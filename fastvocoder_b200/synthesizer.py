@@ -92,6 +92,33 @@ class Synthesizer:
             self.model.inference(mel)
 
 
+def publish_model(checkpoint_path, config_path, model_name, save_path, frames: int = 30000, device="cuda"):
+    """bin/publish.py:18-77: for Basis-MelGAN store the zero-input "pattern" (inference on `frames` all-zero mel frames,
+    i.e. up to 300 s of audio) next to the weights so synthesis can subtract it without a second pass."""
+    with open(config_path) as f:
+        config = yaml.load(f, Loader=yaml.Loader)
+    model = build_generator(model_name, config).to(device)
+    ckpt = torch.load(os.path.join(checkpoint_path), map_location="cpu", weights_only=False)
+    model.load_state_dict(ckpt["model"])
+    if model_name == "basis-melgan":
+        with torch.no_grad():
+            bias = model.inference(torch.zeros(frames, config["in_channels"]))   # (16*frames + 1) * 15 samples
+        torch.save({"model": model.state_dict(), "pattern": bias.cpu().numpy()}, save_path)
+    model.eval()
+    model.remove_weight_norm()
+    return model
+
+
+def run_publisher(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--checkpoint_path", type=str)
+    parser.add_argument("--model_name", type=str)
+    parser.add_argument("--config", type=str)
+    parser.add_argument("--save_path", type=str)
+    args = parser.parse_args(argv)
+    publish_model(args.checkpoint_path, args.config, args.model_name, args.save_path)
+
+
 def load_mel(path):
     """.npy mel, (80, T) or (T, 80) -> (T, 80)   (bin/test.py:110-113 auto-transpose)."""
     mel = np.load(path)

@@ -476,3 +476,35 @@ def test_model_uses_tensor_cores_when_enabled(specs):
     t0 = _lib.lib().fv_tc_launch_count()
     m(mel)
     assert _lib.lib().fv_tc_launch_count() == t0
+
+
+def test_publish_pattern_and_long_utterance(tmp_path, specs):
+    """bin/publish.py: zero-input pattern for a long utterance (here 3000 frames = 30 s; the reference uses 30000), then
+    bin/test.py:82-91 synthesis = inference(mel)[:-L//2] - pattern.  Checked against the CPU port at full length."""
+    import os
+    from conftest import REPO
+    from fastvocoder_b200.synthesizer import Synthesizer, publish_model
+    key = "basis-melgan-light"
+    cfg = specs[key]["config"]
+    m = build_generator("basis-melgan", cfg)
+    w = folded_weights(specs, key)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    m.apply_weight_norm()
+    ckpt = tmp_path / "basis.pth.tar"
+    torch.save({"model": m.state_dict()}, ckpt)
+    pub = tmp_path / "basis.published.pth.tar"
+    frames = 3000
+    publish_model(str(ckpt), os.path.join(REPO, "conf/basis-melgan/light.yaml"), "basis-melgan", str(pub), frames=frames)
+    d = torch.load(pub, map_location="cpu", weights_only=False)
+    assert d["pattern"].shape == ((16 * frames + 1) * 15,)
+    wt = P.to_torch(w)
+    with torch.no_grad():
+        want = P.basis_melgan_inference(wt, cfg, torch.zeros(frames, 80)).numpy()
+    assert np.abs(d["pattern"] - want).max() < TOL
+    syn = Synthesizer(str(pub), os.path.join(REPO, "conf/basis-melgan/light.yaml"), "basis-melgan")
+    mel = synth_mel(1, 120, seed=21)[0].T.copy()
+    est = syn.synthesize_with_pattern(mel)
+    with torch.no_grad():
+        ref = P.basis_melgan_inference(wt, cfg, torch.from_numpy(mel)).numpy()[:-15]
+    assert est.shape[0] == ref.shape[0]
+    assert np.abs(est.cpu().numpy() - (ref - want[: ref.shape[0]])).max() < TOL
