@@ -304,6 +304,7 @@ struct Tc2Args {
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
   int ck, nck;       // K-chunking: an A stage holds `ck` input channels of the tile; nck = Cin / ck stages per tile
+  int cluster_mode;  // experimental (FV_CLUSTER): 1 = pairs, private weight copies; 2 = each CTA multicasts its half; 3 = rank 0 multicasts all
   int n_issuers;     // UMMA issuer warps in use (1..4; at most 3 when the weight ring needs warp 11)
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
   uint32_t idesc;    // M=128, N=NT
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                   if (g >= p.w_stages) {
                     const uint32_t ph = (uint32_t)((g / p.w_stages - 1) & 1);
                     mbar_wait(BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
-                    if (cs > 1) {                                        // ... tell every CTA, then wait for all of them
+                    if (cs > 1 && p.cluster_mode >= 2) {                 // ... tell every CTA, then wait for all of them
                       if (L0) for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(BAR(24 + slot), r);
                       mbar_wait(BAR(24 + slot), ph, 520 + slot);
                     }
@@ -563,11 +564,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                     mbar_expect_tx(BAR(8 + slot), bytes);   // the full stage lands here: my slice + the peers' slices
                     const uint32_t dst = smem_u32(Wbuf + (size_t)slot * p.stage_bytes);
                     const uint8_t* src = wsrc + (size_t)kb0 * kblock_bytes;
-                    if (cs == 1) {
+                    if (cs == 1 || p.cluster_mode == 1) {
                       bulk_g2s(dst, src, bytes, BAR(8 + slot));
-                    } else {
+                    } else if (p.cluster_mode == 2) {
                       const uint32_t slice = bytes / cs;     // k-block bytes are a multiple of 1024
                       bulk_g2s_mcast(dst + cr * slice, src + (size_t)cr * slice, slice, BAR(8 + slot), cmask);
+                    } else if (cr == 0) {
+                      bulk_g2s_mcast(dst, src, bytes, BAR(8 + slot), cmask);
                     }
                   }
                 }
@@ -823,8 +826,9 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
   // EXPERIMENTAL (round 1): the multicast ring produces wrong results on hardware, so it is opt-in until debugged.
-  static const bool use_cluster = getenv("FV_CLUSTER") != nullptr;
-  const int cs = (!p.w_resident && use_cluster && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
+  static const int cluster_mode = getenv("FV_CLUSTER") ? atoi(getenv("FV_CLUSTER")) : 0;
+  const int cs = (!p.w_resident && cluster_mode > 0 && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
+  p.cluster_mode = cs == 2 ? cluster_mode : 0;
   if (cs == 2) gx = (gx + 1) & ~1;   // pairs; an odd tile count leaves one CTA with ring duty only
   if (cs == 2 && gx > num_sms[dev] / L.n_tiles) gx -= 2;
   if (gx < cs) gx = cs;
