@@ -599,10 +599,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
             mbar_wait(BAR(0 + s), (uint32_t)((u / p.a_stages) & 1), 610 + s);
             tc_fence_after();
             const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
-            const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi0 >> 4) + (uint64_t)(wid * 128);
+            const uint64_t ad_mine = a_tmpl + (uint64_t)((a_hi0 >> 4) & 0x3FFF) + (uint64_t)(wid * 128);   // 14-bit field: in a cluster
+            // the shared-window address carries the CTA rank in its upper bits, which must not spill into the LBO field
             // one 16-channel k-block of tap j (k-step ksl inside this chunk) on all my M tiles
             auto do_kblock = [&](int j, int ksl, uint32_t bsm) {
-              const uint64_t bd_hi = b_tmpl + (uint64_t)(bsm >> 4);
+              const uint64_t bd_hi = b_tmpl + (uint64_t)((bsm >> 4) & 0x3FFF);
               const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
               const uint32_t a_off16 = (uint32_t)(2 * ksl) * (uint32_t)rows + (uint32_t)(j * a.dil);   // 16-B units
               const uint32_t first = (ch | j | ksl) ? 1u : 0u;                     // very first k-block of the tile overwrites
@@ -999,10 +1000,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         // one GEMM-conv over a resident weight image: A rows [row0 + j*dil], accumulators at `acc`
         auto run_conv = [&](uint64_t a_tmpl, uint32_t a_hi_addr, uint32_t a_rows, uint32_t a_lo_delta16, uint32_t wsm,
                             int dil, uint32_t acc) {
-          const uint64_t ad_mine = a_tmpl + (uint64_t)(a_hi_addr >> 4) + (uint64_t)(wid * 128);
+          const uint64_t ad_mine = a_tmpl + (uint64_t)((a_hi_addr >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
           int j = 0, ks = 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint64_t bd_hi = b_tmpl + (uint64_t)((wsm + (uint32_t)kb * kblock_bytes) >> 4);
+            const uint64_t bd_hi = b_tmpl + (uint64_t)(((wsm + (uint32_t)kb * kblock_bytes) >> 4) & 0x3FFF);
             const uint32_t a_off16 = (uint32_t)(2 * ks) * a_rows + (uint32_t)(j * dil);
             const uint32_t first = kb > 0 ? 1u : 0u;
             uint64_t ad_hi = ad_mine + a_off16;
