@@ -89,6 +89,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
   }
 }
+// Stall accounting (FV_STALL_DEBUG=1 builds of the persistent kernels): per role, cycles spent in each class of
+// mbarrier wait, total cycles in the role loop and tiles walked -> dbg[(cta * 8 + role) * 8 + slot].
+template <bool DBG>
+struct WaitAcc {
+  long long w[5];
+  long long t0;
+  __device__ __forceinline__ void begin() {
+    if (DBG) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) w[i] = 0;
+      t0 = clock64();
+    }
+  }
+  __device__ __forceinline__ void wait(int k, uint32_t bar, uint32_t parity, int tag) {
+    if (DBG) {
+      const long long t = clock64();
+      mbar_wait(bar, parity, tag);
+      w[k] += clock64() - t;
+    } else {
+      mbar_wait(bar, parity, tag);
+    }
+  }
+  __device__ __forceinline__ void end(long long* dbg, int role, bool writer, long long tiles) {
+    if (DBG) {
+      if (dbg && writer) {
+        long long* o = dbg + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * 8 + role) * 8;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) o[i] = w[i];
+        o[5] = clock64() - t0;
+        o[6] = tiles;
+      }
+    }
+  }
+};
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -114,6 +148,28 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Converged-warp issue: every lane of the (fully converged) issuer warp executes this, one elected lane issues.
+// With warp-uniform operands the compiler keeps descriptors in uniform registers and emits a bare UTCHMMA — no
+// per-instruction ELECT / BRA.U.ANY "waterfall" and no divergent-branch bookkeeping (scripts/probes/umma_issue_probe.cu:
+// 40 clk per N=32 UMMA, the shared-memory operand floor, against 150-250 clk for a loop with per-UMMA index math).
+__device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// tcgen05.commit tracks the MMAs of the EXECUTING thread: it must come from the same elected lane (elect.sync is
+// deterministic for a given member mask).
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -296,6 +352,32 @@ constexpr int TC2_LOADER_WARPS = 8;
 constexpr int TC2_ISSUE_WARPS = 4;    // warps 8..11: UMMA issuers (warp 11 doubles as the weight producer)
 constexpr int TC2_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 4) * 32;  // 8 loaders + 4 issue/producer + 4 epilogue
 
+// `nkb` consecutive 16-channel k-blocks (A advances ks_step16, weights advance kb16 per block) on MT M tiles of this
+// issuer (A rows mt_step16 / accumulator columns d_step apart).  Everything is warp-uniform; MT is unrolled so the
+// per-UMMA overhead is one or two uniform adds.  DUAL: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs per block,
+// hi*lo terms in their own accumulator columns); else three N = NT UMMAs into the same columns.
+template <bool DUAL, int MT>
+__device__ __forceinline__ void issue_kblocks(uint64_t ad, uint64_t bd, uint32_t d0, int nkb, uint32_t accum,
+                                              uint64_t ks_step16, uint64_t kb16, uint64_t mt_step16, uint32_t d_step,
+                                              uint64_t lo_delta16, uint64_t nt16, uint32_t idesc, uint32_t idesc2) {
+  for (int q = 0; q < nkb; ++q, ad += ks_step16, bd += kb16) {
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const uint64_t am = ad + (uint64_t)m * mt_step16;
+      const uint32_t d = d0 + (uint32_t)m * d_step;
+      if (DUAL) {
+        umma_f16_elect(d, am, bd, idesc2, accum);               // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+        umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);      // lo*hi -> cols [0,NT)
+      } else {
+        umma_f16_elect(d, am, bd, idesc, accum);
+        umma_f16_elect(d, am, bd + nt16, idesc, 1u);            // + NT*16 bytes: the lo half of the block
+        umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);
+      }
+    }
+    accum = 1u;
+  }
+}
+
 struct Tc2Args {
   ConvArgs a;
   const uint8_t* wimg;
@@ -309,18 +391,20 @@ struct Tc2Args {
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
   uint32_t idesc;    // M=128, N=NT
   uint32_t idesc2;   // M=128, N=2*NT (dual)
+  long long* dbg;    // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// Epilogue of one CTA tile for layers WITHOUT a residual / running-sum addend (any output layout):
+// tcgen05.ld -> + bias -> [tanh] -> coalesced stores (ConvTranspose: phase interleave; narrow layers: masked tail columns).
 template <int LAYOUT>
 __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
                                                   int nt) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
-  const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
   const int nchunks = p.NT >> 4;
   for (int c = 0; c < nchunks; ++c) {
     const int nbase = nt * p.NT + c * 16;
@@ -375,28 +459,6 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
       float v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rr[i]) + bias[i];
-      if (rb) {
-        float rv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rv[i] = __ldg(rb + o0 + i * ostride);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += rv[i];
-      }
-      if (a.acc_mode != ACC_STORE) {
-        float yv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) yv[i] = yb[o0 + i * ostride];
-        if (a.acc_mode == ACC_ADD) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = yv[i] + v[i];
-        } else {
-          // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division,
-          // far inside the 1e-4 budget, and ~10 instructions per element cheaper (this launch was 2x its siblings)
-          const float inv = 1.0f / a.acc_div;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = (yv[i] + v[i]) * inv;
-        }
-      }
       if (a.post_tanh) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
@@ -407,6 +469,64 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
   }
 }
 
+// Epilogue for [B, C, L] layers WITH an addend from global memory: y = conv + bias + residual [+ running MRF sum,
+// / num_kernels].  The addend does not depend on the accumulators, so its loads are issued before the TMEM read:
+// one memory latency per (chunk, M tile) instead of two or three back to back.  (No padded-N layers here: run_layer.)
+__device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
+                                                      int nt) {
+  const ConvArgs& a = p.a;
+  float* __restrict__ yb = a.y + (long long)b * a.y_bs;
+  const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
+  const int nchunks = p.NT >> 4;
+  // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division, far inside 1e-4
+  const float inv = a.acc_mode == ACC_ADD_DIV ? 1.0f / a.acc_div : 1.0f;
+  for (int c = 0; c < nchunks; ++c) {
+    const int nbase = nt * p.NT + c * 16;
+    float bias[16];
+    if (a.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + nbase);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(bp + i);
+        bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+    }
+    for (int mt = 0; mt < p.m_tiles; ++mt) {
+      const int pos = t0 + mt * 128 + q * 32 + lane;
+      const bool ok = pos < a.Lpos;
+      const long long o0 = (long long)nbase * a.Lpos + pos, ostride = a.Lpos;
+      float addend[16];
+      if (rb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) addend[i] = ok ? __ldg(rb + o0 + i * ostride) : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) addend[i] = 0.f;
+      }
+      if (a.acc_mode != ACC_STORE) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) addend[i] += ok ? yb[o0 + i * ostride] : 0.f;
+      }
+      uint32_t rr[16];
+      const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
+      tmem_ld16(tcol, rr);
+      if (p.dual) {
+        uint32_t r2[16];
+        tmem_ld16(tcol + (uint32_t)p.NT, r2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+      }
+      if (!ok) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = ((__uint_as_float(rr[i]) + bias[i]) + addend[i]) * inv;
+    }
+  }
+}
+
+template <bool DBG>
 __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args p) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
@@ -465,13 +585,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     const int nrb = (rows + 127) >> 7;          // row blocks of 128 (4 rows per lane)
     const int npairs = nkc * nrb;
     int u = 0;                                  // A-stage unit counter: (tile, channel chunk)
+    WaitAcc<DBG> wa;
+    wa.begin();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
       for (int ch = 0; ch < p.nck; ++ch, ++u) {
         const int s = u % p.a_stages;
-        if (u >= p.a_stages) mbar_wait(BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
+        if (u >= p.a_stages) wa.wait(0, BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
         uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
         uint8_t* A_lo = A_hi + a_bytes;
         for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
@@ -528,6 +650,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         }
       }
     }
+    wa.end(p.dbg, 0, warp == 0 && lane == 0, u);
   } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weight producer + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;                 // 0..3
@@ -535,6 +658,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     const bool L0 = (lane == 0);   // the whole warp walks the loops (uniform control flow), lane 0 issues
     {
       if (is_producer) {
+        WaitAcc<DBG> wa;
+        wa.begin();
         if (p.w_resident) {
           const uint32_t total = (uint32_t)p.kblocks * kblock_bytes;
           if (L0) mbar_expect_tx(BAR(8), total);
@@ -551,10 +676,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                   const int slot = g % p.w_stages;
                   if (g >= p.w_stages) {
                     const uint32_t ph = (uint32_t)((g / p.w_stages - 1) & 1);
-                    mbar_wait(BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
+                    wa.wait(0, BAR(16 + slot), ph, 500 + slot);          // my issuers are done with the slot
                     if (cs > 1 && p.cluster_mode >= 2) {                 // ... tell every CTA, then wait for all of them
                       if (L0) for (uint32_t r = 0; r < cs; ++r) mbar_arrive_remote(BAR(24 + slot), r);
-                      mbar_wait(BAR(24 + slot), ph, 520 + slot);
+                      wa.wait(1, BAR(24 + slot), ph, 520 + slot);
                     }
                   }
                   const int kb0 = j * p.ksteps + ch * kpc + run * p.kb_per_stage;
@@ -576,12 +701,15 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                 }
           }
         }
+        wa.end(p.dbg, 1, L0, ring_tiles);
       }
       if (wid < p.n_issuers) {   // (in ring mode n_issuers <= 3, so the producer never gets here)
+        WaitAcc<DBG> wa;
+        wa.begin();
         const uint32_t a_lbo = (uint32_t)rows * 16;
         const uint32_t b_lbo = (uint32_t)p.NT * 32;
         const uint32_t wbase = smem_u32(Wbuf);
-        if (p.w_resident) mbar_wait(BAR(8), 0, 600);
+        if (p.w_resident) wa.wait(0, BAR(8), 0, 600);
         // descriptor templates: only the 14-bit start-address field (units of 16 B) changes between UMMAs
         const uint64_t a_tmpl = make_kmajor_desc(0, a_lbo, 128);
         const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
@@ -589,63 +717,73 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         const uint32_t a_lo_delta = a_bytes >> 4;
         const uint32_t mt_step16 = 128u * (uint32_t)p.n_issuers;          // A rows between my consecutive M tiles
         const uint32_t d_step = acc_mt_cols * (uint32_t)p.n_issuers;
+        const uint32_t idesc = p.idesc, idesc2 = p.idesc2;
+        const int K = a.K, dil = a.dil, m_tiles = p.m_tiles, n_iss = p.n_issuers;
+        const bool dual = p.dual != 0, resident = p.w_resident != 0;
+        const uint32_t kb16 = (uint32_t)kblock_bytes >> 4;                  // one weight k-block, in 16-B units
+        const uint64_t nt16 = (uint64_t)p.NT;
+        const uint64_t ks_step16 = 2ull * (uint64_t)rows;                   // next 16-channel k-step of the A stage
+        const int my_mts = (m_tiles - wid + n_iss - 1) / n_iss;             // M tiles wid, wid + n_iss, ... (<= 4, see tc2_plan)
+        __syncwarp();                                                       // elect.sync needs the full warp converged
         int it = 0, g = 0, u = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
           const int as = it % p.acc_stages;
-          if (it >= p.acc_stages) mbar_wait(BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
+          if (it >= p.acc_stages) wa.wait(1, BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
           const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols) + (uint32_t)wid * acc_mt_cols;
           for (int ch = 0; ch < p.nck; ++ch, ++u) {
             const int s = u % p.a_stages;
-            mbar_wait(BAR(0 + s), (uint32_t)((u / p.a_stages) & 1), 610 + s);
+            wa.wait(2, BAR(0 + s), (uint32_t)((u / p.a_stages) & 1), 610 + s);
             tc_fence_after();
             const uint32_t a_hi0 = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
             const uint64_t ad_mine = a_tmpl + (uint64_t)((a_hi0 >> 4) & 0x3FFF) + (uint64_t)(wid * 128);   // 14-bit field: in a cluster
             // the shared-window address carries the CTA rank in its upper bits, which must not spill into the LBO field
             // one 16-channel k-block of tap j (k-step ksl inside this chunk) on all my M tiles
-            auto do_kblock = [&](int j, int ksl, uint32_t bsm) {
-              const uint64_t bd_hi = b_tmpl + (uint64_t)((bsm >> 4) & 0x3FFF);
-              const uint64_t bd_lo = bd_hi + (uint64_t)p.NT;                      // + NT*16 bytes
-              const uint32_t a_off16 = (uint32_t)(2 * ksl) * (uint32_t)rows + (uint32_t)(j * a.dil);   // 16-B units
-              const uint32_t first = (ch | j | ksl) ? 1u : 0u;                     // very first k-block of the tile overwrites
-              uint64_t ad_hi = ad_mine + a_off16;
-              uint32_t d = acc;
-              if (p.dual) {
-                for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                  if (L0) {
-                    umma_f16(d, ad_hi, bd_hi, p.idesc2, first);              // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
-                    umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);     // lo*hi -> cols [0,NT)
-                  }
+            // Tight, warp-converged issue (umma_f16_elect): descriptors advance incrementally in uniform registers.
+            // One 16-channel k-block (A rows at `ad_hi`, weights at `bd_hi`) on all my M tiles:
+            auto do_kblocks = [&](uint64_t ad, uint64_t bd, int nkb, uint32_t accum) {
+#define FV_ISSUE(D, M) issue_kblocks<D, M>(ad, bd, acc, nkb, accum, ks_step16, (uint64_t)kb16, (uint64_t)mt_step16, d_step, \
+                                           (uint64_t)a_lo_delta, nt16, idesc, idesc2)
+              if (dual) {
+                switch (my_mts) {
+                  case 1: FV_ISSUE(true, 1); break;
+                  case 2: FV_ISSUE(true, 2); break;
+                  case 3: FV_ISSUE(true, 3); break;
+                  default: FV_ISSUE(true, 4); break;
                 }
               } else {
-                for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-                  if (L0) {
-                    umma_f16(d, ad_hi, bd_hi, p.idesc, first);
-                    umma_f16(d, ad_hi, bd_lo, p.idesc, 1u);
-                    umma_f16(d, ad_hi + a_lo_delta, bd_hi, p.idesc, 1u);
-                  }
+                switch (my_mts) {
+                  case 1: FV_ISSUE(false, 1); break;
+                  case 2: FV_ISSUE(false, 2); break;
+                  case 3: FV_ISSUE(false, 3); break;
+                  default: FV_ISSUE(false, 4); break;
                 }
               }
+#undef FV_ISSUE
             };
-            for (int j = 0; j < a.K; ++j) {
-              if (p.w_resident) {
-                for (int ksl = 0; ksl < kpc; ++ksl)
-                  do_kblock(j, ksl, wbase + (uint32_t)(j * p.ksteps + ch * kpc + ksl) * kblock_bytes);
+            uint32_t accum = ch ? 1u : 0u;     // the very first k-block of the tile overwrites the accumulators
+            for (int j = 0; j < K; ++j) {
+              uint64_t ad = ad_mine + (uint64_t)(j * dil);                       // tap shift: j*dil rows of 16 B
+              if (resident) {
+                const uint64_t bd = b_tmpl + (uint64_t)(((wbase >> 4) + (uint32_t)(j * p.ksteps + ch * kpc) * kb16) & 0x3FFF);
+                do_kblocks(ad, bd, kpc, accum);
+                accum = 1u;
               } else {
                 for (int run = 0; run < runs_per_grp; ++run, ++g) {
                   const int slot = g % p.w_stages;
-                  mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
+                  wa.wait(3, BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 630 + slot);
                   tc_fence_after();
                   const int nkb = min(p.kb_per_stage, kpc - run * p.kb_per_stage);
-                  for (int qk = 0; qk < nkb; ++qk)
-                    do_kblock(j, run * p.kb_per_stage + qk,
-                              wbase + (uint32_t)slot * p.stage_bytes + (uint32_t)qk * kblock_bytes);
-                  if (L0) umma_commit(BAR(16 + slot));   // local; the producers exchange "slot free" across the cluster
+                  const uint64_t bd = b_tmpl + (uint64_t)(((wbase + (uint32_t)slot * p.stage_bytes) >> 4) & 0x3FFF);
+                  do_kblocks(ad, bd, nkb, accum);
+                  accum = 1u;
+                  ad += (uint64_t)nkb * ks_step16;
+                  umma_commit_elect(BAR(16 + slot));   // local; the producers exchange "slot free" across the cluster
                 }
               }
             }
-            if (L0) umma_commit(BAR(2 + s));    // this A stage may be overwritten once these UMMAs have read it
+            umma_commit_elect(BAR(2 + s));    // this A stage may be overwritten once these UMMAs have read it
           }
-          if (L0) umma_commit(BAR(4 + as));     // my accumulators of this tile are complete
+          umma_commit_elect(BAR(4 + as));     // my accumulators of this tile are complete
         }
         // a cluster peer may have one more tile than I do: keep consuming / releasing the shared weight ring
         if (!p.w_resident) {
@@ -653,11 +791,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
           for (int rt = it; rt < ring_tiles; ++rt) {
             for (int wi = 0; wi < iters_per_tile; ++wi, ++g) {
               const int slot = g % p.w_stages;
-              mbar_wait(BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 640 + slot);
-              if (L0) umma_commit(BAR(16 + slot));
+              wa.wait(4, BAR(8 + slot), (uint32_t)((g / p.w_stages) & 1), 640 + slot);
+              umma_commit_elect(BAR(16 + slot));
             }
           }
         }
+        wa.end(p.dbg, 2, wid == 0 && L0, it);
       }
     }
     __syncwarp();
@@ -665,20 +804,24 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     // ------------------------------------------------------------------ epilogue warps (4 consecutive warps)
     const int q = warp & 3;
     int it = 0;
+    WaitAcc<DBG> wa;
+    wa.begin();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it % p.acc_stages;
-      mbar_wait(BAR(4 + as), (uint32_t)((it / p.acc_stages) & 1), 700 + as);
+      wa.wait(0, BAR(4 + as), (uint32_t)((it / p.acc_stages) & 1), 700 + as);
       tc_fence_after();
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
-      if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL>(p, acc, q, lane, b, t0, nt);
+      if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) tc2_epilogue_tile_add(p, acc, q, lane, b, t0, nt);
+      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL>(p, acc, q, lane, b, t0, nt);
       else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC>(p, acc, q, lane, b, t0, nt);
       else tc2_epilogue_tile<OUT_PHASE>(p, acc, q, lane, b, t0, nt);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(6 + as));
     }
+    wa.end(p.dbg, 3, q == 0 && lane == 0, it);
   }
   tc_fence_before();
   __syncthreads();
@@ -703,62 +846,81 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const long long w_total = (long long)kblocks * kblock_bytes;
   const long long BUDGET = 225 * 1024;
   const int need_mt = (a.Lpos + 127) / 128;
-  const int dualf = (NT <= 128) ? 2 : 1;
-  // cycles for the 3 logical passes of one k-block on one M tile: math vs operand fetch (~128 B/clk of smem)
-  const double c_mma3 = dualf == 2
-      ? std::max((double)NT, (4096.0 + NT * 64.0) / 128.0) + std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0)
-      : 3.0 * std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
-  struct Cand { int mt, a_st, res, w_st, ck, kbps; double score; };
-  Cand best{0, 0, 0, 0, 0, 0, -1.0};
-  // Cycle model per CTA tile, calibrated on B200 profiles (profiles/r01_notes.md):
-  //   loaders ~14 B/clk of fp32 input (DRAM-latency bound, 8 warps x 32 loads in flight),
+  static const int force_dual = getenv("FV_TC2_DUAL") ? atoi(getenv("FV_TC2_DUAL")) : -1;   // tuning knob: 0 / 1
+  if ((a.res != nullptr || a.acc_mode != ACC_STORE) && (a.out_layout != OUT_BCL || a.post_tanh)) return false;
+  struct Cand { int mt, a_st, res, w_st, ck, kbps, dual; double score; };
+  Cand best{0, 0, 0, 0, 0, 0, 0, -1.0};
+  // Cycle model per CTA tile, calibrated on B200 (profiles/r01_notes.md, scripts/probes/umma_issue_probe.cu and the
+  // FV_STALL_DEBUG role accounting):
+  //   UMMA M=128 K=16: max(N/2, (4096 + 32 N)/128) clk — math vs the 128 B/clk shared-memory operand fetch; a tight
+  //     issue loop costs ~20 clk per UMMA per issuer thread,
+  //   loaders ~8 B/clk of fp32 input (DRAM-latency bound, 8 warps x 32 loads in flight),
   //   weight ring: bytes in flight / ~2500-cycle bulk-copy round trip, capped at ~14 B/clk per SM (all SMs stream the
-  //   same image from L2: ~4 TB/s aggregate measured) -> ring-mode layers want the largest M per weight pass,
-  //   epilogue ~40 B/clk of output traffic.
+  //     same image from L2) -> ring-mode layers want the largest M per weight pass,
+  //   epilogue: 0.34 clk per output element, +0.47 with a residual read, +0.74 with the MRF read-modify-write
+  //     (latency-bound global accesses of 4 warps); it overlaps the MMAs only with two accumulator sets.
   const int ck_opts[4] = {a.Cin, 128, 64, 32};
-  for (int cki = 0; cki < 4; ++cki) {
-    const int ck = ck_opts[cki];
-    if (ck > a.Cin || a.Cin % ck || ck % 16 || (cki > 0 && ck == a.Cin)) continue;
-    const int nck = a.Cin / ck, kpc = ck / 16;
-    int kbps = 16384 / kblock_bytes;
-    if (kbps < 1) kbps = 1;
-    if (kbps > kpc) kbps = kpc;
-    const int stage_bytes = kbps * kblock_bytes;
-    for (int res = 1; res >= 0; --res)
-      for (int a_st = 2; a_st >= 1; --a_st)
-        for (int mt = 8; mt >= 1; --mt) {
-          if (mt * NT * dualf > 512) continue;
-          if (mt > need_mt && mt > 1) continue;
-          if (nck > 1 && a_st < 2) continue;    // chunking only pays with double-buffered stages
-          for (int w_st = (res ? 1 : 8); w_st >= (res ? 1 : 2); --w_st) {
-            const long long wb = res ? w_total : (long long)w_st * stage_bytes;
-            const long long a_stage = 2LL * (mt * 128 + halo) * ck * 2;
-            if (a_st * a_stage + wb + 512 > BUDGET) continue;
-            const bool acc2 = 2 * mt * NT * dualf <= 512;
-            const double t_mma = (double)kblocks * mt * c_mma3;
-            // loaders: each of the 8 warps handles (8 channels x 128 rows) per round; a round costs one DRAM round trip
-            const int rows_t = mt * 128 + halo;
-            const int pairs = (ck / 8) * ((rows_t + 127) / 128);
-            const double t_load = nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
-            const double ring_bw = std::min(14.0, (double)wb / 2500.0);   // measured: ~14 B/clk/SM when every SM streams the same image
-            const double t_w = res ? 0.0 : (double)w_total / ring_bw;
-            const double t_epi = (double)mt * 128 * NT * 4.0 * (1 + (a.res != nullptr) + (a.acc_mode != ACC_STORE)) / 40.0 + 600.0;
-            const double t_core = std::max(t_mma, t_w);
-            double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
-            t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
-            t_tile += 3000.0;   // measured fixed cost per tile (barrier hand-offs, pipeline bubbles)
-            const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
-            long long gx = std::max(1, num_sms / L.n_tiles);
-            if (gx > tiles) gx = tiles;
-            const long long waves = (tiles + gx - 1) / gx;
-            const double tail_eff = (double)tiles / (double)(waves * gx);
-            const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);
-            const double sc = useful / t_tile * tail_eff;
-            if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, ck, kbps, sc};
+  for (int df = 2; df >= 1; --df) {
+    if (df == 2 && NT > 128) continue;
+    if (force_dual >= 0 && NT <= 128 && (df == 2) != (force_dual != 0)) continue;
+    // measured on B200 (history #12): [B_hi|B_lo] N-doubling wins for NT < 128 (fewer, longer UMMAs against the smem operand
+    // floor); for NT = 128 the three-UMMA form costs the same tensor time and leaves room for two accumulator sets
+    if (force_dual < 0 && (df == 2) != (NT < 128)) continue;
+    const double c_pipe = df == 2
+        ? std::max((double)NT, (4096.0 + NT * 64.0) / 128.0) + std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0)
+        : 3.0 * std::max(NT / 2.0, (4096.0 + NT * 32.0) / 128.0);
+    const double n_umma = df == 2 ? 2.0 : 3.0;
+    for (int cki = 0; cki < 4; ++cki) {
+      const int ck = ck_opts[cki];
+      if (ck > a.Cin || a.Cin % ck || ck % 16 || (cki > 0 && ck == a.Cin)) continue;
+      const int nck = a.Cin / ck, kpc = ck / 16;
+      int kbps = 16384 / kblock_bytes;
+      if (kbps < 1) kbps = 1;
+      if (kbps > kpc) kbps = kpc;
+      const int stage_bytes = kbps * kblock_bytes;
+      for (int res = 1; res >= 0; --res)
+        for (int a_st = 2; a_st >= 1; --a_st)
+          for (int mt = 8; mt >= 1; --mt) {
+            if (mt * NT * df > 512) continue;
+            if (mt > need_mt && mt > 1) continue;
+            if (nck > 1 && a_st < 2) continue;    // chunking only pays with double-buffered stages
+            for (int w_st = (res ? 1 : 8); w_st >= (res ? 1 : 2); --w_st) {
+              const long long wb = res ? w_total : (long long)w_st * stage_bytes;
+              const long long a_stage = 2LL * (mt * 128 + halo) * ck * 2;
+              if (a_st * a_stage + wb + 512 > BUDGET) continue;
+              const bool acc2 = 2 * mt * NT * df <= 512;
+              int ni = res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1;
+              if (ni > mt) ni = mt;
+              if (NT * df >= 256 && ni > 2) ni = 2;
+              const int my_mts = (mt + ni - 1) / ni;
+              if (my_mts > 4) continue;
+              const double t_mma = std::max((double)kblocks * mt * c_pipe, (double)kblocks * my_mts * n_umma * 20.0);
+              const int rows_t = mt * 128 + halo;
+              const int pairs = (ck / 8) * ((rows_t + 127) / 128);
+              const double t_load = nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
+              const double ring_bw = std::min(14.0, (double)wb / 2500.0);
+              const double t_w = res ? 0.0 : (double)w_total / ring_bw;
+              const double t_epi = (double)mt * 128 * NT *
+                                       (0.34 + (a.res != nullptr ? 0.47 : 0.0) + (a.acc_mode != ACC_STORE ? 0.74 : 0.0)) +
+                                   600.0;
+              const double t_core = std::max(t_mma, t_w);
+              double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
+              t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
+              t_tile += 3000.0;   // measured fixed cost per tile (barrier hand-offs, pipeline bubbles)
+              const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
+              long long gx = std::max(1, num_sms / L.n_tiles);
+              if (gx > tiles) gx = tiles;
+              const long long waves = (tiles + gx - 1) / gx;
+              const double tail_eff = (double)tiles / (double)(waves * gx);
+              const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);
+              const double sc = useful / t_tile * tail_eff;
+              if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, ck, kbps, df, sc};
+            }
           }
-        }
+    }
   }
   if (best.score < 0) return false;
+  const int dualf = best.dual;
   p.a = a;
   p.NT = NT;
   p.m_tiles = best.mt;
@@ -772,7 +934,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.stage_bytes = best.kbps * kblock_bytes;
   p.ck = best.ck;
   p.nck = a.Cin / best.ck;
-  {  // issuers: short UMMAs (narrow N) are issue-bound -> spread M tiles over several issuer warps
+  {  // issuers: each owns the M tiles wid, wid + n, ... (its own accumulators)
     int ni = best.res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1;
     if (ni > best.mt) ni = best.mt;
     if (NT * dualf >= 256 && ni > 2) ni = 2;   // long UMMAs: the tensor pipe, not the issue slot, is the limit
@@ -802,6 +964,50 @@ inline void tc_apply_env_once() {
   }
 }
 
+// FV_STALL_DEBUG=1: launch the instrumented instantiation, synchronise and print where each role waited (stderr).
+inline bool tc_stall_debug() {
+  static const bool on = getenv("FV_STALL_DEBUG") != nullptr && atoi(getenv("FV_STALL_DEBUG")) != 0;
+  return on;
+}
+struct StallReport {
+  long long* dev = nullptr;
+  int ctas = 0;
+  bool begin(int n_ctas) {
+    ctas = n_ctas;
+    if (cudaMalloc(&dev, (size_t)ctas * 64 * sizeof(long long)) != cudaSuccess) return false;
+    return cudaMemset(dev, 0, (size_t)ctas * 64 * sizeof(long long)) == cudaSuccess;
+  }
+  // role_names[r] / slot_names[r][k]: nullptr-terminated labels
+  void finish(cudaStream_t st, const char* title, const char* const* role_names, const char* const (*slot_names)[5]) {
+    cudaStreamSynchronize(st);
+    std::vector<long long> h((size_t)ctas * 64);
+    cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    dev = nullptr;
+    fprintf(stderr, "[stall] %s ctas=%d\n", title, ctas);
+    for (int r = 0; r < 8; ++r) {
+      if (!role_names[r]) continue;
+      double tot = 0, tiles = 0, w[5] = {0, 0, 0, 0, 0};
+      int n = 0;
+      for (int c = 0; c < ctas; ++c) {
+        const long long* o = &h[((size_t)c * 8 + r) * 8];
+        if (o[5] == 0) continue;
+        ++n; tot += (double)o[5]; tiles += (double)o[6];
+        for (int k = 0; k < 5; ++k) w[k] += (double)o[k];
+      }
+      if (!n) continue;
+      fprintf(stderr, "[stall]   %-9s total %9.0f clk  units %6.1f", role_names[r], tot / n, tiles / n);
+      double ws = 0;
+      for (int k = 0; k < 5; ++k) {
+        if (!slot_names[r][k]) continue;
+        fprintf(stderr, "  %s %5.1f%%", slot_names[r][k], 100.0 * w[k] / tot);
+        ws += w[k];
+      }
+      fprintf(stderr, "  busy %5.1f%% (%.0f clk/unit)\n", 100.0 * (tot - ws) / tot, tiles > 0 ? (tot - ws) / tiles : 0.0);
+    }
+  }
+};
+
 inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
   tc_apply_env_once();
   static int num_sms[64] = {};
@@ -819,7 +1025,8 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   p.wimg = L.image;
   const size_t smem = tc2_smem_bytes(p);
   if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return -1;
     attr_set[dev] = true;
   }
@@ -845,7 +1052,28 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel, p);
+  cudaError_t le;
+  if (tc_stall_debug()) {
+    StallReport rep;
+    if (!rep.begin(gx * L.n_tiles)) return -1;
+    p.dbg = rep.dev;
+    le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, p);
+    static const char* const roles[8] = {"loader", "producer", "issuer0", "epilogue", nullptr, nullptr, nullptr, nullptr};
+    static const char* const slots[8][5] = {{"a_empty", nullptr, nullptr, nullptr, nullptr},
+                                            {"w_empty", "w_free", nullptr, nullptr, nullptr},
+                                            {"w_res", "acc_empty", "a_full", "w_full", "w_drain"},
+                                            {"acc_full", nullptr, nullptr, nullptr, nullptr}};
+    char title[256];
+    snprintf(title, sizeof title,
+             "tc2 Cin=%d N=%d K=%d dil=%d Lpos=%d B=%d layout=%d res=%d acc=%d | NT=%d mt=%d ck=%d a_st=%d acc_st=%d "
+             "resident=%d w_st=%d kbps=%d issuers=%d dual=%d tiles=%d grid=%dx%d",
+             a.Cin, a.N, a.K, a.dil, a.Lpos, a.B, a.out_layout, a.res != nullptr, a.acc_mode, p.NT, p.m_tiles, p.ck,
+             p.a_stages, p.acc_stages, p.w_resident, p.w_stages, p.kb_per_stage, p.n_issuers, p.dual, p.total_tiles, gx,
+             L.n_tiles);
+    rep.finish(st, title, roles, slots);
+  } else {
+    le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false>, p);
+  }
   g_launches++;
   g_tc_launches++;
   return (le == cudaSuccess && cudaGetLastError() == cudaSuccess) ? 0 : -1;
@@ -882,8 +1110,27 @@ struct Tc3Args {
   int ksteps, kblocks;
   int tiles_per_batch, total_tiles;
   uint32_t idesc, idesc2;
+  long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
+// One issuer's UMMAs of a whole K-tap conv on ONE M tile, k-steps unrolled (KS = Cin/16): per tap the loop body is
+// 2*KS UTCHMMAs plus two uniform adds.  dual layout: [hi*hi | hi*lo] with N = 2*NT, then lo*hi with N = NT.
+template <int KS>
+__device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_t d, int K, uint64_t tap_step16,
+                                               uint64_t ks_step16, uint64_t kb_step16, uint64_t lo_delta16,
+                                               uint32_t idesc, uint32_t idesc2) {
+  uint32_t accum = 0u;
+  for (int j = 0; j < K; ++j, ad += tap_step16, bd += KS * kb_step16) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      umma_f16_elect(d, ad + ks * ks_step16, bd + ks * kb_step16, idesc2, accum);
+      umma_f16_elect(d, ad + ks * ks_step16 + lo_delta16, bd + ks * kb_step16, idesc, 1u);
+      accum = 1u;
+    }
+  }
+}
+
+template <bool DBG>
 __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
@@ -936,9 +1183,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     const int nrb = (rows + 127) >> 7;
     const int npairs = nkc * nrb;
     int it = 0;
+    WaitAcc<DBG> wa;
+    wa.begin();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int s = it % p.a1_stages;
-      if (it >= p.a1_stages) mbar_wait(BAR(2 + s), (uint32_t)((it / p.a1_stages - 1) & 1), 800 + s);
+      if (it >= p.a1_stages) wa.wait(0, BAR(2 + s), (uint32_t)((it / p.a1_stages - 1) & 1), 800 + s);
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       const float* __restrict__ xb = p.x + (long long)b * C * p.L;
@@ -974,6 +1223,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(0 + s));
     }
+    wa.end(p.dbg, 0, warp == 0 && lane == 0, it);
   } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weights (once) + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;
@@ -988,7 +1238,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         }
       }
       if (wid < p.n_issuers) {
-        mbar_wait(BAR(14), 0, 810);
+        WaitAcc<DBG> wa;
+        wa.begin();
+        wa.wait(0, BAR(14), 0, 810);
         const uint32_t b_lbo = (uint32_t)NT * 32;
         const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
         const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows * 16, 128);
@@ -998,56 +1250,65 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         const uint32_t d_step = mt_cols * (uint32_t)p.n_issuers;
         const uint32_t w1s = smem_u32(W1), w2s = smem_u32(W2);
         // one GEMM-conv over a resident weight image: A rows [row0 + j*dil], accumulators at `acc`
+        // Tight issue loop: all descriptor arithmetic is incremental and warp-uniform (uniform registers), the whole
+        // warp walks it converged and one elected lane issues (umma_f16_elect).
+        const uint32_t idesc = p.idesc, idesc2 = p.idesc2;
+        const int K = p.K, ksteps = p.ksteps, m_tiles = p.m_tiles, n_iss = p.n_issuers;
+        const uint64_t kb_step16 = (uint64_t)(kblock_bytes >> 4);
         auto run_conv = [&](uint64_t a_tmpl, uint32_t a_hi_addr, uint32_t a_rows, uint32_t a_lo_delta16, uint32_t wsm,
                             int dil, uint32_t acc) {
-          const uint64_t ad_mine = a_tmpl + (uint64_t)((a_hi_addr >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
-          int j = 0, ks = 0;
-          for (int kb = 0; kb < p.kblocks; ++kb) {
-            const uint64_t bd_hi = b_tmpl + (uint64_t)(((wsm + (uint32_t)kb * kblock_bytes) >> 4) & 0x3FFF);
-            const uint32_t a_off16 = (uint32_t)(2 * ks) * a_rows + (uint32_t)(j * dil);
-            const uint32_t first = kb > 0 ? 1u : 0u;
-            uint64_t ad_hi = ad_mine + a_off16;
-            uint32_t d = acc + (uint32_t)wid * mt_cols;
-            for (int mt = wid; mt < p.m_tiles; mt += p.n_issuers, ad_hi += mt_step16, d += d_step) {
-              if (L0) {
-                umma_f16(d, ad_hi, bd_hi, p.idesc2, first);
-                umma_f16(d, ad_hi + a_lo_delta16, bd_hi, p.idesc, 1u);
+          const uint64_t ad0 = a_tmpl + (uint64_t)((a_hi_addr >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
+          uint64_t bd = b_tmpl + (uint64_t)((wsm >> 4) & 0x3FFF);
+          const uint32_t d0 = acc + (uint32_t)wid * mt_cols;
+          const uint64_t ks_step16 = (uint64_t)(2u * a_rows);
+          const uint64_t lo_delta = (uint64_t)a_lo_delta16;
+          if (m_tiles <= n_iss) {   // one M tile per issuer (every plan tc3_plan makes): k-steps unrolled
+            if (ksteps == 1) { issue_conv_1mt<1>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
+            if (ksteps == 2) { issue_conv_1mt<2>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
+            if (ksteps == 4) { issue_conv_1mt<4>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
+          }
+          uint32_t accum = 0u;
+          for (int j = 0; j < K; ++j) {
+            uint64_t ad = ad0 + (uint64_t)(j * dil);
+            for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bd += kb_step16) {
+              uint64_t a = ad;
+              uint32_t d = d0;
+              for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) {
+                umma_f16_elect(d, a, bd, idesc2, accum);
+                umma_f16_elect(d, a + lo_delta, bd, idesc, 1u);
               }
+              accum = 1u;
             }
-            if (++ks == p.ksteps) { ks = 0; ++j; }
           }
         };
         int n_my = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) ++n_my;
         auto conv1 = [&](int i) {
           const int s = i % p.a1_stages, as = i % p.acc1_stages;
-          mbar_wait(BAR(0 + s), (uint32_t)((i / p.a1_stages) & 1), 820 + s);
-          if (i >= p.acc1_stages) mbar_wait(BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
+          wa.wait(1, BAR(0 + s), (uint32_t)((i / p.a1_stages) & 1), 820 + s);
+          if (i >= p.acc1_stages) wa.wait(2, BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
           tc_fence_after();
           run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w1s, p.dil,
                    tmem_base + (uint32_t)(as * p.acc_cols));
-          if (L0) {
-            umma_commit(BAR(2 + s));
-            umma_commit(BAR(4 + as));
-          }
+          umma_commit_elect(BAR(2 + s));
+          umma_commit_elect(BAR(4 + as));
         };
         auto conv2 = [&](int i) {
           const int bs = i & 1;   // acc2 is double buffered: epiB(i-1) overlaps conv2(i)
-          mbar_wait(BAR(8), (uint32_t)(i & 1), 840);
-          if (i >= 2) mbar_wait(BAR(12 + bs), (uint32_t)((i / 2 - 1) & 1), 850 + bs);
+          wa.wait(3, BAR(8), (uint32_t)(i & 1), 840);
+          if (i >= 2) wa.wait(4, BAR(12 + bs), (uint32_t)((i / 2 - 1) & 1), 850 + bs);
           tc_fence_after();
           run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1,
                    acc2_base + (uint32_t)(bs * p.acc_cols));
-          if (L0) {
-            umma_commit(BAR(9));
-            umma_commit(BAR(10 + bs));
-          }
+          umma_commit_elect(BAR(9));
+          umma_commit_elect(BAR(10 + bs));
         };
         if (n_my > 0) conv1(0);
         for (int i = 0; i < n_my; ++i) {
           if (i + 1 < n_my) conv1(i + 1);
           conv2(i);
         }
+        wa.end(p.dbg, 2, wid == 0 && L0, n_my);
       }
     }
     __syncwarp();
@@ -1058,13 +1319,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     uint8_t* A2_hi = A2;
     uint8_t* A2_lo = A2 + a2_bytes;
     int it = 0;
+    WaitAcc<DBG> wa;
+    wa.begin();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       {  // ---- epiA: acc1 -> +b1 -> lrelu -> fp16 split -> A2 (zero rows outside the sequence: conv2's zero padding)
         const int as = it % p.acc1_stages;
-        mbar_wait(BAR(4 + as), (uint32_t)((it / p.acc1_stages) & 1), 860 + as);
-        if (it >= 1) mbar_wait(BAR(9), (uint32_t)((it - 1) & 1), 870);
+        wa.wait(0, BAR(4 + as), (uint32_t)((it / p.acc1_stages) & 1), 860 + as);
+        if (it >= 1) wa.wait(1, BAR(9), (uint32_t)((it - 1) & 1), 870);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
         for (int c = 0; c < nchunks; ++c) {
@@ -1105,11 +1368,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         }
       }
     }
+    wa.end(p.dbg, 4, q == 0 && lane == 0, it);
   } else {
     // ------------------------------------------------------------------ epiB warps: acc2 -> global
     const int q = warp & 3;
     const int nchunks = NT >> 4;
     int it = 0;
+    WaitAcc<DBG> wa;
+    wa.begin();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
@@ -1138,7 +1404,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               for (int i = 0; i < 16; ++i) xv[i] += ok ? yb[o0 + (long long)i * p.L] : 0.f;
             }
             if (!waited) {
-              mbar_wait(BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
+              wa.wait(0, BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
               tc_fence_after();
               waited = true;
             }
@@ -1164,6 +1430,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         if (lane == 0) mbar_arrive(BAR(12 + bs));
       }
     }
+    wa.end(p.dbg, 5, q == 0 && lane == 0, it);
   }
   tc_fence_before();
   __syncthreads();
@@ -1182,9 +1449,13 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   const long long BUDGET = 225 * 1024;
   int best_m = 0, best_a1 = 0, best_acc1 = 0;
   double best_sc = -1;
+  static const int force_m_env = getenv("FV_TC3_M") ? atoi(getenv("FV_TC3_M")) : 0;   // tuning knob
+  int force_m = force_m_env;
+retry:
   for (int acc1 = 2; acc1 >= 1; --acc1)
     for (int a1 = 2; a1 >= 1; --a1)
       for (int m = 8; m >= 1; --m) {
+        if (force_m > 0 && m != force_m) continue;
         if ((acc1 + 2) * m * 2 * C > 512) continue;
         const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
         const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + 2LL * kblocks * C * 64 + 256;
@@ -1200,6 +1471,7 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
         sc *= (m >= 2 ? 1.0 : 0.9);
         if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; }
       }
+  if (best_sc < 0 && force_m > 0) { force_m = 0; goto retry; }   // forced tile count infeasible for this width
   if (best_sc < 0) return false;
   p.B = B; p.C = C; p.L = L; p.K = K; p.dil = dil;
   p.m_tiles = best_m;
@@ -1209,6 +1481,8 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   p.a1_stages = best_a1;
   p.acc1_stages = best_acc1;
   p.n_issuers = std::min(best_m, TC2_ISSUE_WARPS);
+  static const int force_iss = getenv("FV_TC3_ISSUERS") ? atoi(getenv("FV_TC3_ISSUERS")) : 0;   // tuning knob
+  if (force_iss > 0) p.n_issuers = std::max(1, std::min(p.n_issuers, force_iss));
   p.acc_cols = best_m * 2 * C;
   int cols = 32;
   while (cols < (best_acc1 + 2) * p.acc_cols) cols <<= 1;
@@ -1239,8 +1513,10 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
   cudaGetDevice(&dev);
   dev &= 63;
   if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(conv_tc3_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc3_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc3_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+            cudaSuccess)
       return -1;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
@@ -1248,7 +1524,26 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     attr_set[dev] = true;
   }
   int gx = std::min(num_sms[dev], p.total_tiles);
-  conv_tc3_fused_kernel<<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
+  if (tc_stall_debug()) {
+    StallReport rep;
+    if (!rep.begin(gx)) return -1;
+    p.dbg = rep.dev;
+    conv_tc3_fused_kernel<true><<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
+    static const char* const roles[8] = {"loader", nullptr, "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
+    static const char* const slots[8][5] = {{"a1_empty", nullptr, nullptr, nullptr, nullptr},
+                                            {nullptr, nullptr, nullptr, nullptr, nullptr},
+                                            {"w_full", "a1_full", "acc1_empty", "a2_full", "acc2_empty"},
+                                            {nullptr, nullptr, nullptr, nullptr, nullptr},
+                                            {"acc1_full", "a2_empty", nullptr, nullptr, nullptr},
+                                            {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
+    char title[256];
+    snprintf(title, sizeof title,
+             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d issuers=%d tiles=%d grid=%d", C,
+             K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.n_issuers, p.total_tiles, gx);
+    rep.finish(st, title, roles, slots);
+  } else {
+    conv_tc3_fused_kernel<false><<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
+  }
   g_launches++;
   g_tc_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -49,6 +49,7 @@ class Synthesizer:
     def __init__(self, checkpoint_path, config_path, model_name, device="cuda") -> None:
         self.device = torch.device(device)
         self.pattern = None
+        self._bias_cache = {}     # (frames, weights version) -> zero-input waveform on the device
         self.model = self.load_model(checkpoint_path, config_path, model_name)
 
     def load_model(self, checkpoint_path, config_path, model_name):
@@ -67,11 +68,25 @@ class Synthesizer:
         model.remove_weight_norm()
         return model
 
+    def zero_input_bias(self, frames: int) -> torch.Tensor:
+        """`model.inference(zeros(frames, 80))` — the input-independent "bias" waveform of bin/synthesize.py:76-78.
+        It depends on the weights and on `frames` only, so it is computed once per length and kept on the device
+        (the reference recomputes it on every call; bin/publish.py:67-75 caches the same thing as `pattern`)."""
+        key = (int(frames), self.model.packed_weights._version)
+        hit = self._bias_cache.get(key)
+        if hit is None:
+            with torch.no_grad():
+                hit = self.model.inference(torch.zeros(int(frames), NUM_MELS))
+            if len(self._bias_cache) >= 64:          # bounded: drop the oldest length
+                self._bias_cache.pop(next(iter(self._bias_cache)))
+            self._bias_cache[key] = hit
+        return hit
+
     def synthesize(self, mel):
         """mel: (T, 80) ndarray -> (est_source, est_source - bias, bias)   (bin/synthesize.py:74-80)."""
         with torch.no_grad():
-            zero_mel = torch.zeros_like(torch.from_numpy(np.asarray(mel)).float())
-            bias = self.model.inference(zero_mel)
+            frames = int(np.asarray(mel).shape[0]) if not isinstance(mel, torch.Tensor) else int(mel.shape[0])
+            bias = self.zero_input_bias(frames)
             est_source = self.model.inference(mel)
             est_source_remove_bias = est_source - bias
         return est_source, est_source_remove_bias, bias
