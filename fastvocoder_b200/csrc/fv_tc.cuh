@@ -400,9 +400,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Epilogue of one CTA tile for layers WITHOUT a residual / running-sum addend (any output layout):
 // tcgen05.ld -> + bias -> [tanh] -> coalesced stores (ConvTranspose: phase interleave; narrow layers: masked tail columns).
-template <int LAYOUT>
+template <int LAYOUT, bool DBG>
 __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                  int nt) {
+                                                  int nt, WaitAcc<DBG>& wa) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const int nchunks = p.NT >> 4;
@@ -426,6 +426,8 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
       const int pos = t0 + mt * 128 + q * 32 + lane;
       uint32_t rr[16];
       const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
+      long long tdbg = 0;
+      if (DBG) tdbg = clock64();
       tmem_ld16(tcol, rr);
       if (p.dual) {  // columns [NT, 2NT) hold the separately accumulated hi*lo terms
         uint32_t r2[16];
@@ -433,6 +435,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
 #pragma unroll
         for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
       }
+      if (DBG) { const long long t1 = clock64(); wa.w[1] += t1 - tdbg; tdbg = t1; }   // "tmem": TMEM read + wait::ld
       long long o0, ostride;
       bool ok = pos < a.Lpos;
       if (LAYOUT == OUT_BCL) {
@@ -465,6 +468,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = v[i];
+      if (DBG) wa.w[4] += clock64() - tdbg;      // "store": bias add + issuing the 16 stores
     }
   }
 }
@@ -472,57 +476,86 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
 // Epilogue for [B, C, L] layers WITH an addend from global memory: y = conv + bias + residual [+ running MRF sum,
 // / num_kernels].  The addend does not depend on the accumulators, so its loads are issued before the TMEM read:
 // one memory latency per (chunk, M tile) instead of two or three back to back.  (No padded-N layers here: run_layer.)
+template <bool DBG>
 __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                      int nt) {
+                                                      int nt, WaitAcc<DBG>& wa) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
   const int nchunks = p.NT >> 4;
+  const int n_it = nchunks * p.m_tiles;          // iteration = (chunk c, M tile mt), mt fastest
   // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division, far inside 1e-4
   const float inv = a.acc_mode == ACC_ADD_DIV ? 1.0f / a.acc_div : 1.0f;
-  for (int c = 0; c < nchunks; ++c) {
+  const long long ostride = a.Lpos;
+  const int row = q * 32 + lane;
+  // The residual of iteration it+1 is requested before iteration it is processed (software pipelining: two sets of
+  // loads in flight per warp instead of one; these four warps are latency-bound, not bandwidth-bound).
+  float nxt[16];
+  {
+    const bool ok0 = t0 + row < a.Lpos;
+    const long long o = (long long)(nt * p.NT) * a.Lpos + t0 + row;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok0) ? __ldg(rb + o + i * ostride) : 0.f;
+  }
+  int c = 0, mt = 0;
+  for (int it = 0; it < n_it; ++it) {
     const int nbase = nt * p.NT + c * 16;
-    float bias[16];
-    if (a.bias) {
-      const float4* bp = reinterpret_cast<const float4*>(a.bias + nbase);
+    const int pos = t0 + mt * 128 + row;
+    const bool ok = pos < a.Lpos;
+    const long long o0 = (long long)nbase * a.Lpos + pos;
+    float addend[16];
+    long long tld = 0;
+    if (DBG) tld = clock64();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldg(bp + i);
-        bias[4 * i] = v.x; bias[4 * i + 1] = v.y; bias[4 * i + 2] = v.z; bias[4 * i + 3] = v.w;
-      }
-    } else {
+    for (int i = 0; i < 16; ++i) addend[i] = nxt[i];
+    int c2 = c, mt2 = mt + 1;
+    if (mt2 == p.m_tiles) { mt2 = 0; ++c2; }
+    if (it + 1 < n_it) {
+      const int pos2 = t0 + mt2 * 128 + row;
+      const bool ok2 = pos2 < a.Lpos;
+      const long long o2 = (long long)(nt * p.NT + c2 * 16) * a.Lpos + pos2;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+      for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok2) ? __ldg(rb + o2 + i * ostride) : 0.f;
     }
-    for (int mt = 0; mt < p.m_tiles; ++mt) {
-      const int pos = t0 + mt * 128 + q * 32 + lane;
-      const bool ok = pos < a.Lpos;
-      const long long o0 = (long long)nbase * a.Lpos + pos, ostride = a.Lpos;
-      float addend[16];
-      if (rb) {
+    if (a.acc_mode != ACC_STORE) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) addend[i] = ok ? __ldg(rb + o0 + i * ostride) : 0.f;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) addend[i] = 0.f;
-      }
-      if (a.acc_mode != ACC_STORE) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) addend[i] += ok ? yb[o0 + i * ostride] : 0.f;
-      }
-      uint32_t rr[16];
-      const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
-      tmem_ld16(tcol, rr);
-      if (p.dual) {
-        uint32_t r2[16];
-        tmem_ld16(tcol + (uint32_t)p.NT, r2);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
-      }
-      if (!ok) continue;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = ((__uint_as_float(rr[i]) + bias[i]) + addend[i]) * inv;
+      for (int i = 0; i < 16; ++i) addend[i] += ok ? yb[o0 + i * ostride] : 0.f;
     }
+    uint32_t rr[16];
+    const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
+    long long tdbg = 0;
+    if (DBG) { tdbg = clock64(); wa.w[3] += tdbg - tld; }   // "ldissue": issuing the residual / running-sum loads
+    tmem_ld16(tcol, rr);
+    if (p.dual) {
+      uint32_t r2[16];
+      tmem_ld16(tcol + (uint32_t)p.NT, r2);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+    }
+    if (DBG) {
+      const long long t1 = clock64();
+      wa.w[1] += t1 - tdbg;                      // "tmem": TMEM read + wait::ld
+      float sink = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) sink += addend[i];
+      if (sink == 123.456f) wa.w[4] += 1;         // forces the addend loads to have landed
+      tdbg = clock64();
+      wa.w[2] += tdbg - t1;                      // "addwait": residual / running-sum loads still in flight after the TMEM read
+    }
+    if (ok) {
+      if (a.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(a.bias + nbase);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 bv = __ldg(bp + i4);
+          addend[4 * i4] += bv.x; addend[4 * i4 + 1] += bv.y; addend[4 * i4 + 2] += bv.z; addend[4 * i4 + 3] += bv.w;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = (__uint_as_float(rr[i]) + addend[i]) * inv;
+    }
+    if (DBG) wa.w[4] += clock64() - tdbg;        // "store": bias add + issuing the 16 stores
+    c = c2; mt = mt2;
   }
 }
 
@@ -813,10 +846,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
-      if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) tc2_epilogue_tile_add(p, acc, q, lane, b, t0, nt);
-      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL>(p, acc, q, lane, b, t0, nt);
-      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC>(p, acc, q, lane, b, t0, nt);
-      else tc2_epilogue_tile<OUT_PHASE>(p, acc, q, lane, b, t0, nt);
+      if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) tc2_epilogue_tile_add<DBG>(p, acc, q, lane, b, t0, nt, wa);
+      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa);
+      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa);
+      else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(6 + as));
@@ -1062,7 +1095,7 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
     static const char* const slots[8][5] = {{"a_empty", nullptr, nullptr, nullptr, nullptr},
                                             {"w_empty", "w_free", nullptr, nullptr, nullptr},
                                             {"w_res", "acc_empty", "a_full", "w_full", "w_drain"},
-                                            {"acc_full", nullptr, nullptr, nullptr, nullptr}};
+                                            {"acc_full", "tmem", "addwait", "ldissue", "store"}};
     char title[256];
     snprintf(title, sizeof title,
              "tc2 Cin=%d N=%d K=%d dil=%d Lpos=%d B=%d layout=%d res=%d acc=%d | NT=%d mt=%d ck=%d a_st=%d acc_st=%d "
@@ -1222,6 +1255,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(0 + s));
+      // epiB of this tile (two tiles from now) adds the running MRF sum y: a DRAM read its 4 warps cannot hide.
+      // Pull those lines into L2 now (x itself was just read by this loop, so the residual is an L2 hit already).
+      if (p.acc_mode != ACC_STORE) {
+        const int lines_per_row = (p.m_out * 4 + 127) >> 7;
+        const int total = C * lines_per_row;
+        const float* __restrict__ yb = p.y + (long long)b * C * p.L;
+        for (int i = warp * 32 + lane; i < total; i += TC2_LOADER_WARPS * 32) {
+          const int n = i / lines_per_row, ln = i - n * lines_per_row;
+          const long long pos = (long long)t0 + ln * 32;
+          if (pos < p.L) asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + (long long)n * p.L + pos));
+        }
+      }
     }
     wa.end(p.dbg, 0, warp == 0 && lane == 0, it);
   } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
