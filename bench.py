@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "audio samples/sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "model": name, "frames": T,
+        "config": {"workload": label, "generator": name, "frames": T,
                    "note": "reference CPU path = ATen conv ops on host cores (oracle/torch_port.py); "
                            f"each step = {sample_utts} of the {B} utterances"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
@@ -349,7 +349,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tcgen05 layers: fp16 hi+lo split x3, fp32 accumulate)" if not args.no_tc else "f32",
             "data": "synthetic",
-            "config": {"workload": label, "model": name, "yaml": ypath, "batch_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": label, "generator": name, "yaml": ypath, "batch_per_gpu": B, "global_batch": B * world,
                        "frames": T, "parallelism": f"batch-shard x{world}", "l2": "explicit 256 MiB flush between timed steps",
                        "timing": "cuda events per step, max over ranks"},
             "rtf": t_dev / args.steps / (B * T * 0.01),

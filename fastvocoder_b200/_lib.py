@@ -76,6 +76,7 @@ SIGNATURES = {
     "fv_out_length": (_I, [_P, _I, _I, C.POINTER(C.c_int64)]),
     "fv_workspace_bytes": (_I, [_P, _I, _I, C.POINTER(C.c_size_t)]),
     "fv_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, C.c_size_t, _I, _P]),
+    "fv_forward_ragged": (_I, [_P, _P, _I, _I, C.POINTER(C.c_int32), _P, _P, _P, C.c_size_t, _I, _P]),
     "fv_forward_flops": (_I, [_P, _I, _I, _I, C.POINTER(C.c_double)]),
     "fv_forward_profile": (_I, [_P, _P, _I, _I, _P, _P, _P, C.c_size_t, _I, _P, C.POINTER(FvProfileEntry), _I,
                                 C.POINTER(_I)]),

@@ -97,6 +97,7 @@ struct LayerCall {
   bool allow_tc = true;
   const float* x2 = nullptr;   // L_PAIR: second input (the un-activated stack input for the skip layer)
   float pre_slope2 = -1.f;
+  const int* lens = nullptr;   // ragged batches: valid input length per utterance (device), or nullptr
 };
 
 static long long layer_out_len(const Layer& l, long long Lin) {
@@ -113,6 +114,7 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   a.B = c.B; a.Cin = l.Cin; a.N = l.N; a.Lin = (int)c.Lin; a.K = l.Kd; a.dil = l.dil;
   a.pad_mode = c.pad_mode; a.pre_slope = c.pre_slope;
   a.acc_mode = c.acc_mode; a.acc_div = c.acc_div; a.post_tanh = c.post_tanh;
+  a.lens = c.lens;
   a.x_bs = c.x_bs >= 0 ? c.x_bs : (long long)l.Cin * c.Lin;
   long long out_per_b;
   if (l.type == L_CONV) {
@@ -202,8 +204,11 @@ struct Profiler {
   std::vector<Rec> recs;
 };
 
+static size_t lens_floats(int Be) { return ((size_t)(FV_MAX_STAGES + 2) * Be + 63) / 64 * 64; }
+
 static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* ws,
-                        size_t ws_bytes, int flags, cudaStream_t st, Profiler* prof = nullptr) {
+                        size_t ws_bytes, int flags, cudaStream_t st, Profiler* prof = nullptr,
+                        const int32_t* lens_host = nullptr) {
   const Model& m = h->model;
   const fv_config& c = m.cfg;
   static const bool tc_disabled_env = getenv("FV_DISABLE_TC") != nullptr;
@@ -214,7 +219,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   const int Be = eff_batch(m, B, flags);
   const size_t each = max_act_floats(m, Be, T);
   const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
-  const size_t need = (6 * each + mel_ext_floats) * sizeof(float);
+  const size_t need = (6 * each + mel_ext_floats + (lens_host ? lens_floats(Be) : 0)) * sizeof(float);
   if (ws_bytes < need) return fail(FV_ENOMEM, "workspace too small: have %zu need %zu", ws_bytes, need);
   float* base = (float*)ws;
   float* bufA = base;
@@ -224,6 +229,30 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   float* bufU1 = base + 4 * each;
   float* bufY = base + 5 * each;
   float* mel_ext = base + 6 * each;
+  // Ragged batch: per-utterance valid lengths at the input (row 0) and after every upsample stage (rows 1..), on the
+  // device.  Every kernel treats samples at or beyond its utterance's length as sequence padding, so utterance b
+  // gets exactly what a B=1 call with T = lens[b] computes; the tail of each row is computed but meaningless.
+  int* lens_dev = nullptr;
+  if (lens_host) {
+    if (Be != B) return fail(FV_EINVAL, "ragged Basis-MelGAN batches need FV_FWD_BASIS_INFERENCE (one pass, no zero-input subtraction)");
+    std::vector<int> hl((m.stages.size() + 1) * (size_t)B);
+    for (int b = 0; b < B; ++b) {
+      long long l = lens_host[b];
+      if (l <= 0 || l > T || (!m.is_hifi() && l <= (c.pre_kernel_size - 1) / 2))
+        return fail(FV_EINVAL, "lens[%d] = %lld out of range for T = %d", b, l, T);
+      hl[b] = (int)l;
+      for (size_t s = 0; s < m.stages.size(); ++s) {
+        l = Model::convt_out_len(m.layers[m.stages[s].up], l);
+        if (l <= 0) return fail(FV_EINVAL, "lens[%d] too short for this architecture", b);
+        hl[(s + 1) * B + b] = (int)l;
+      }
+    }
+    lens_dev = reinterpret_cast<int*>(mel_ext + mel_ext_floats);
+    FV_CUDA(cudaMemcpyAsync(lens_dev, hl.data(), hl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  auto lens_at = [&](int stage_out, int b0) -> const int* {   // stage_out = -1: mel / conv_pre; s: after upsample stage s
+    return lens_dev ? lens_dev + (size_t)(stage_out + 1) * B + b0 : nullptr;
+  };
 
   auto wd = [&](int li) { return h->derived + m.layers[li].wd_offset; };
   auto bias = [&](int li) -> const float* {
@@ -260,7 +289,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   float* other = bufB;
   {  // conv_pre (hifigan.py:93, zero pad) / ReflectionPad1d + Conv1d (melgan.py:68-71)
     LayerCall lc;
-    lc.x = x_in; lc.y = cur; lc.B = Be; lc.Lin = L;
+    lc.x = x_in; lc.y = cur; lc.B = Be; lc.Lin = L; lc.lens = lens_at(-1, 0);
     lc.pad_mode = m.is_hifi() ? PAD_ZERO : PAD_REFLECT;
     if ((rc = call(m.pre, lc))) return rc;
   }
@@ -286,10 +315,11 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       float* s_out = other + (long long)b0 * out_per_utt;   // this micro-batch's slice of the stage output
       {  // LeakyReLU + ConvTranspose1d
         LayerCall lc;
-        lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L;
+        lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L; lc.lens = lens_at((int)s - 1, b0);
         lc.pre_slope = m.is_hifi() ? 0.1f : 0.2f;  // LRELU_SLOPE modules.py:9 / negative_slope 0.2 melgan.py:30
         if ((rc = call(sg.up, lc))) return rc;
       }
+      const int* sl = lens_at((int)s, b0);   // lengths of this stage's tensors
       if (m.is_hifi()) {
         // MRF: xs = sum_j resblock_j(y); x = xs / num_kernels (hifigan.py:97-103); s_out accumulates xs.
         const int nb_br = (int)sg.branches.size();
@@ -316,7 +346,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                     cudaEventRecord(r.e0, st);
                   }
                   const int frc = launch_fused_unit(bc, dst, bias(br.units[u].c1), bias(br.units[u].c2), *t1, *t2, nb,
-                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st);
+                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st, sl);
                   if (prof) {
                     if (frc == 0) { cudaEventRecord(r.e1, st); prof->recs.push_back(r); }
                     else { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -326,15 +356,15 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                 }
               }
               LayerCall l1;
-              l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
+              l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f; l1.lens = sl;
               if ((rc = call(br.units[u].c1, l1))) return rc;
               LayerCall l2;
-              l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.1f;
+              l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.1f; l2.lens = sl;
               l2.acc_mode = acc; l2.acc_div = div;
               if ((rc = call(br.units[u].c2, l2))) return rc;
             } else {  // ResBlock2 unit (modules.py:248-251)
               LayerCall l1;
-              l1.x = bc; l1.y = dst; l1.res = bc; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
+              l1.x = bc; l1.y = dst; l1.res = bc; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f; l1.lens = sl;
               l1.acc_mode = acc; l1.acc_div = div;
               if ((rc = call(br.units[u].c1, l1))) return rc;
             }
@@ -351,19 +381,19 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
           const Stack& sk = sg.stacks[k];
           float* dst = (k == ns - 1) ? s_out : (k % 2 ? bufY : bufU1);
           LayerCall l1;
-          l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT;
+          l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT; l1.lens = sl;
           if ((rc = call(sk.dil_conv, l1))) return rc;
           if (pair_ok && sk.pair >= 0) {   // stack.4(lrelu(h)) + skip_layer(c) as one two-input 1x1 GEMM-conv
             LayerCall lp;
             lp.x = bufH; lp.pre_slope = 0.2f; lp.x2 = sc_in; lp.pre_slope2 = -1.f;
-            lp.y = dst; lp.B = nb; lp.Lin = Lout;
+            lp.y = dst; lp.B = nb; lp.Lin = Lout; lp.lens = sl;
             if ((rc = call(sk.pair, lp))) return rc;
           } else {
             LayerCall ls;
-            ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout;
+            ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout; ls.lens = sl;
             if ((rc = call(sk.skip, ls))) return rc;
             LayerCall l2;
-            l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f;
+            l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f; l2.lens = sl;
             if ((rc = call(sk.conv1x1, l2))) return rc;
           }
           sc_in = dst;
@@ -377,19 +407,21 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   if (m.is_hifi()) {  // F.leaky_relu(x) [slope 0.01!] -> conv_post -> tanh (hifigan.py:104-106)
     LayerCall lc;
     lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = 0.01f; lc.post_tanh = 1;
+    lc.lens = lens_at((int)m.stages.size() - 1, 0);
     if ((rc = call(m.post, lc))) return rc;
     if (c.kind == FV_MB_HIFIGAN && out2) {
       if (!h->pqmf_syn) return fail(FV_ESTATE, "PQMF synthesis filter not bound");
       const int S = c.pqmf_subbands;
       dim3 grid(grid_for(L * S), B);
-      pqmf_synthesis_kernel<<<grid, 256, S * (c.pqmf_taps + 1) * sizeof(float), st>>>(out, h->pqmf_syn, out2, S,
-                                                                                     c.pqmf_taps, (int)L);
+      pqmf_synthesis_kernel<<<grid, 256, S * (c.pqmf_taps + 1) * sizeof(float), st>>>(
+          out, h->pqmf_syn, out2, S, c.pqmf_taps, (int)L, lens_at((int)m.stages.size() - 1, 0));
       g_launches++;
       FV_CUDA(cudaGetLastError());
     }
   } else if (c.kind == FV_MELGAN) {  // LastLayer (modules.py:85-89) + Tanh (melgan.py:109-110)
     LayerCall lc;
     lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = 0.2f; lc.pad_mode = PAD_REFLECT;
+    lc.lens = lens_at((int)m.stages.size() - 1, 0);
     lc.post_tanh = c.use_final_activation ? 1 : 0;
     if ((rc = call(m.post, lc))) return rc;
   } else {  // ReLU -> Linear(C->L) -> overlap_and_add(L/2)  (basis_melgan.py:121, modules.py:264-267)
@@ -397,6 +429,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     const long long full_len = (L + 1) * bl.N;
     LayerCall lc;
     lc.x = cur; lc.B = Be; lc.Lin = L; lc.pre_slope = c.use_final_activation ? 0.f : -1.f;
+    lc.lens = lens_at((int)m.stages.size() - 1, 0);
     if (flags & FV_FWD_BASIS_INFERENCE) {
       lc.y = out;
       if ((rc = call(m.basis, lc))) return rc;
@@ -546,7 +579,7 @@ int fv_workspace_bytes(const fv_handle* h, int B, int T, size_t* bytes) {
   const int Be = h->model.cfg.kind == FV_BASIS_MELGAN ? B + 1 : B;
   const size_t each = max_act_floats(h->model, Be, T);
   const size_t mel_ext = ((size_t)Be * h->model.cfg.in_channels * T + 63) / 64 * 64;
-  *bytes = (6 * each + mel_ext) * sizeof(float);
+  *bytes = (6 * each + mel_ext + lens_floats(Be)) * sizeof(float);   // incl. room for a ragged batch's length table
   return FV_OK;
 }
 
@@ -559,6 +592,16 @@ int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* 
     return fail(FV_EINVAL, "ReflectionPad1d needs T > %d", (h->model.cfg.pre_kernel_size - 1) / 2);
   if (h->model.out_length(T, flags) <= 0) return fail(FV_EINVAL, "T too small for this architecture");
   return forward_impl(h, mel, B, T, out, out2, workspace, workspace_bytes, flags, (cudaStream_t)stream);
+}
+
+int fv_forward_ragged(fv_handle* h, const float* mel, int B, int T, const int32_t* lens_host, float* out, float* out2,
+                      void* workspace, size_t workspace_bytes, int flags, void* stream) {
+  if (!h || !mel || !out || !workspace || !lens_host) return fail(FV_EINVAL, "null argument");
+  if (!h->bound) return fail(FV_ESTATE, "fv_forward_ragged before fv_bind_weights");
+  if (B <= 0 || T <= 0) return fail(FV_EINVAL, "B and T must be > 0");
+  if (h->model.out_length(T, flags) <= 0) return fail(FV_EINVAL, "T too small for this architecture");
+  return forward_impl(h, mel, B, T, out, out2, workspace, workspace_bytes, flags, (cudaStream_t)stream, nullptr,
+                      lens_host);
 }
 
 int fv_forward_profile(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,

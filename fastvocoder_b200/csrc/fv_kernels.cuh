@@ -37,6 +37,9 @@ struct ConvArgs {
   int cin_split;
   float pre_slope2;
   long long x2_bs;
+  // ragged batches: valid input length of utterance b (<= Lin; Lin stays the row stride). nullptr = all Lin.
+  // Samples at or beyond lens[b] are treated exactly like the padding beyond the end of the sequence.
+  const int* lens;
 };
 
 // LeakyReLU with 0 <= slope <= 1 (slope 0 = ReLU) is max(v, slope*v); slope < 0 means "no activation".
@@ -80,6 +83,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
 
   const float* xb = a.x + (long long)b * a.x_bs;
   const int wrow = a.K * CO_T;
+  const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;
 
   for (int ci0 = 0; ci0 < a.Cin; ci0 += CI_C) {
     {  // x tile: warp `warp` stages channel ci0+warp (CI_C == 8 warps)
@@ -94,10 +98,10 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
         int g = t0 - a.pad_left + s;
         if (a.pad_mode == PAD_REFLECT) {
           if (g < 0) g = -g;
-          if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+          if (g >= Lb) g = 2 * (Lb - 1) - g;
         }
         float v = 0.f;
-        if (cok && g >= 0 && g < a.Lin) v = pre_act(__ldg(xr + g), slope);
+        if (cok && g >= 0 && g < Lb) v = pre_act(__ldg(xr + g), slope);
         row[s] = v;
       }
     }
@@ -184,12 +188,13 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvArgs a) {
   const int b = blockIdx.y;
   const float* xb = a.x + (long long)b * a.x_bs;
   float* yb = a.y + (long long)b * a.y_bs;
+  const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < a.Lpos; t += gridDim.x * blockDim.x) {
     float acc[NOUT];
 #pragma unroll
     for (int n = 0; n < NOUT; ++n) acc[n] = 0.f;
     const int g0 = t - a.pad_left;
-    const bool interior = g0 >= 0 && g0 + (a.K - 1) * a.dil < a.Lin;   // no padding involved: skip the checks
+    const bool interior = g0 >= 0 && g0 + (a.K - 1) * a.dil < Lb;   // no padding involved: skip the checks
     for (int ci = 0; ci < a.Cin; ++ci) {
       const float* xr = xb + (long long)ci * a.Lin;
       const float* wr = smem + ci * a.K * NOUT;
@@ -204,9 +209,9 @@ __global__ void __launch_bounds__(256) conv_narrow_kernel(const ConvArgs a) {
           int g = g0 + j * a.dil;
           if (a.pad_mode == PAD_REFLECT) {
             if (g < 0) g = -g;
-            if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+            if (g >= Lb) g = 2 * (Lb - 1) - g;
           }
-          const float xv = (g >= 0 && g < a.Lin) ? pre_act(__ldg(xr + g), a.pre_slope) : 0.f;
+          const float xv = (g >= 0 && g < Lb) ? pre_act(__ldg(xr + g), a.pre_slope) : 0.f;
 #pragma unroll
           for (int n = 0; n < NOUT; ++n) acc[n] = fmaf(wr[j * NOUT + n], xv, acc[n]);
         }
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(256) conv_narrow_v4_kernel(const ConvArgs a) {
 
 inline bool conv_narrow_v4_ok(const ConvArgs& a) {
   // window index q + j + off must stay in [0, 12): off = 4 - pad_left in [0,4], 3 + (K-1) + off <= 11
-  return a.dil == 1 && a.pad_mode == PAD_ZERO && a.K <= 8 && a.pad_left <= 4 && (a.K - 1) + (4 - a.pad_left) <= 8 &&
+  return a.lens == nullptr && a.dil == 1 && a.pad_mode == PAD_ZERO && a.K <= 8 && a.pad_left <= 4 && (a.K - 1) + (4 - a.pad_left) <= 8 &&
          a.Lin % 4 == 0 && a.Lpos == a.Lin && a.x_bs % 4 == 0 && a.y_bs % 4 == 0 &&
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
 }
@@ -394,7 +399,7 @@ __global__ void derive_basis_kernel(const float* __restrict__ w, float* __restri
 // synthesis: y[t] = sum_k sum_{j : (t+j-P) % S == 0, 0 <= (t+j-P)/S < Lb} (S*x[k,(t+j-P)/S]) * h[k,j],  P = taps/2
 // ---------------------------------------------------------------------------------------------
 __global__ void pqmf_synthesis_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ y,
-                                      int S, int taps, int Lb) {
+                                      int S, int taps, int Lb, const int* __restrict__ lens = nullptr) {
   extern __shared__ float sh[];  // [S][taps+1]
   const int nt = taps + 1;
   for (int i = threadIdx.x; i < S * nt; i += blockDim.x) sh[i] = h[i];
@@ -403,6 +408,7 @@ __global__ void pqmf_synthesis_kernel(const float* __restrict__ x, const float* 
   const long long L = (long long)Lb * S;
   const int P = taps / 2;
   const float scale = (float)S;
+  const int Lv = lens ? __ldg(lens + b) : Lb;   // ragged batches: sub-band samples beyond the utterance are zero
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
     // smallest j >= 0 with (t + j - P) % S == 0
     long long u = t - P;
@@ -413,7 +419,7 @@ __global__ void pqmf_synthesis_kernel(const float* __restrict__ x, const float* 
       const float* hk = sh + k * nt;
       for (int j = j0; j < nt; j += S) {
         const long long n = (u + j) / S;
-        if (n >= 0 && n < Lb) acc = fmaf(scale * __ldg(xk + n), hk[j], acc);
+        if (n >= 0 && n < Lv) acc = fmaf(scale * __ldg(xk + n), hk[j], acc);
       }
     }
     y[(long long)b * L + t] = acc;

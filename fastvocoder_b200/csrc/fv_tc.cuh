@@ -624,6 +624,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
+      const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;   // ragged batches: valid length of this utterance
       for (int ch = 0; ch < p.nck; ++ch, ++u) {
         const int s = u % p.a_stages;
         if (u >= p.a_stages) wa.wait(0, BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
@@ -645,9 +646,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
             int g = t0 - a.pad_left + r;
             if (a.pad_mode == PAD_REFLECT) {
               if (g < 0) g = -g;
-              if (g >= a.Lin) g = 2 * (a.Lin - 1) - g;
+              if (g >= Lb) g = 2 * (Lb - 1) - g;
             }
-            const bool ok = r < rows && g >= 0 && g < a.Lin;
+            const bool ok = r < rows && g >= 0 && g < Lb;
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * a.Lin + g) : 0.f;
           }
@@ -1130,6 +1131,7 @@ struct Tc3Args {
   float* y;            // [B, C, L]
   const float* bias1;  // conv1 bias or nullptr
   const float* bias2;
+  const int* lens;     // ragged batches: valid length per utterance (<= L), or nullptr
   const uint8_t* w1img;
   const uint8_t* w2img;
   int B, C, L, K, dil;
@@ -1224,6 +1226,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       const float* __restrict__ xb = p.x + (long long)b * C * p.L;
+      const int Lb = p.lens ? __ldg(p.lens + b) : p.L;
       uint8_t* A_hi = A1 + (size_t)s * 2 * a1_bytes;
       uint8_t* A_lo = A_hi + a1_bytes;
       for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
@@ -1236,7 +1239,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           const int r = rbk * 128 + t * 32 + lane;
           rrow[t] = r;
           const int g = t0 - p2 - p1 + r;
-          const bool ok = r < rows && g >= 0 && g < p.L;
+          const bool ok = r < rows && g >= 0 && g < Lb;
 #pragma unroll
           for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * p.L + g) : 0.f;
         }
@@ -1369,6 +1372,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
+      const int Lb = p.lens ? __ldg(p.lens + b) : p.L;
       {  // ---- epiA: acc1 -> +b1 -> lrelu -> fp16 split -> A2 (zero rows outside the sequence: conv2's zero padding)
         const int as = it % p.acc1_stages;
         wa.wait(0, BAR(4 + as), (uint32_t)((it / p.acc1_stages) & 1), 860 + as);
@@ -1382,7 +1386,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           for (int mt = 0; mt < p.m_tiles; ++mt) {
             const int r = mt * 128 + q * 32 + lane;
             const int gpos = t0 - p2 + r;
-            const bool inside = gpos >= 0 && gpos < p.L;
+            const bool inside = gpos >= 0 && gpos < Lb;
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
             tmem_ld16(tcol, rr);
@@ -1544,12 +1548,12 @@ retry:
 // returns 0 launched, 1 not applicable, -1 CUDA error
 inline int launch_fused_unit(const float* x, float* y, const float* b1, const float* b2, const TcLayer& l1,
                              const TcLayer& l2, int B, int C, int L, int K, int dil, float slope, int acc_mode,
-                             float acc_div, cudaStream_t st) {
+                             float acc_div, cudaStream_t st, const int* lens = nullptr) {
   if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
   tc_apply_env_once();
   Tc3Args p{};
   if (!tc3_plan(B, C, L, K, dil, p)) return 1;
-  p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2;
+  p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2; p.lens = lens;
   p.w1img = l1.image; p.w2img = l2.image;
   p.slope = slope; p.acc_mode = acc_mode; p.acc_div = acc_div;
   static bool attr_set[64] = {};

@@ -219,6 +219,49 @@ class _NativeGenerator(torch.nn.Module):
                                              _lib.ptr(ws), ws.numel(), flags, _lib.current_stream_ptr()),
                        "fv_forward")
 
+    def inference_batch(self, mels):
+        """Ragged batch: a list of (T_i, in_channels) mels (ndarray / tensor, lengths may differ) -> list of 1-D
+        waveforms, utterance i being what ``inference(mels[i])`` returns — but ONE launch chain over the padded
+        batch (fv_forward_ragged) instead of the per-file loop of bin/test.py:123-131.  Each kernel treats
+        samples beyond an utterance's own length as sequence padding (zero / reflect about ITS end), so there
+        are no edge artefacts from the padding.  Multi-band: PQMF-synthesised waveform; Basis-MelGAN:
+        ``inference`` semantics (untruncated, no zero-input subtraction)."""
+        if len(mels) == 0:
+            return []
+        self._ensure_bound()
+        dev = self.device
+        ts = [m if isinstance(m, torch.Tensor) else torch.as_tensor(np.asarray(m)) for m in mels]
+        for t in ts:
+            if t.dim() != 2 or t.shape[1] != self._cfg.in_channels:
+                raise RuntimeError(f"expected (T, {self._cfg.in_channels}) mels, got {tuple(t.shape)}")
+        lens = [int(t.shape[0]) for t in ts]
+        B, T = len(ts), max(lens)
+        x = torch.zeros(B, self._cfg.in_channels, T, dtype=torch.float32, device=dev)
+        for i, t in enumerate(ts):
+            x[i, :, : lens[i]] = t.to(dev).float().transpose(0, 1)
+        kind = self._cfg.kind
+        flags = _lib.FV_FWD_BASIS_INFERENCE if kind == _lib.FV_BASIS_MELGAN else 0
+        if not self.use_tensor_cores:
+            flags |= _lib.FV_FWD_NO_TENSOR_CORES
+        n = self.out_length(T, flags)
+        oc = self._cfg.out_channels if kind in (_lib.FV_MB_HIFIGAN, _lib.FV_MELGAN) else 1
+        out = torch.empty(B, oc, n, device=dev, dtype=torch.float32)
+        wav = torch.empty(B, 1, oc * n, device=dev, dtype=torch.float32) if kind == _lib.FV_MB_HIFIGAN else None
+        ws = self._get_workspace(B, T)
+        lens_c = (C.c_int32 * B)(*lens)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fv_forward_ragged(self._handle, _lib.ptr(x), B, T, lens_c, _lib.ptr(out),
+                                                    _lib.ptr(wav), _lib.ptr(ws), ws.numel(), flags,
+                                                    _lib.current_stream_ptr()), "fv_forward_ragged")
+        res = []
+        for i, l in enumerate(lens):
+            ni = self.out_length(l, flags)
+            if kind == _lib.FV_MB_HIFIGAN:
+                res.append(wav[i, 0, : oc * ni].clone())
+            else:
+                res.append(out[i, 0, :ni].clone())
+        return res
+
     def profile_forward(self, x, flags: int = 0):
         """One forward with per-layer CUDA-event timing (fv_forward_profile). Returns a list of dicts."""
         x = self._prep_input(x)

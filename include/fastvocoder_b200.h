@@ -129,6 +129,13 @@ int fv_out_length(const fv_handle* h, int T, int flags, int64_t* out_len);
 int fv_workspace_bytes(const fv_handle* h, int B, int T, size_t* bytes);
 int fv_forward(fv_handle* h, const float* mel, int B, int T, float* out, float* out2, void* workspace,
                size_t workspace_bytes, int flags, void* stream);
+/* Ragged batch <- the per-file loop of bin/test.py:123-131 / bin/synthesize.py:74-80 done as ONE launch chain:
+ * B utterances of lens_host[b] <= T mel frames, packed in mel [B, in_channels, T] (contents at or beyond lens_host[b]
+ * are ignored).  Utterance b receives exactly what fv_forward(B = 1, T = lens_host[b]) computes for it: the first
+ * fv_out_length(lens_host[b]) samples of its row of `out` (rows are fv_out_length(T) long; the tail is unspecified).
+ * lens_host is a HOST array (copied to the device on `stream`).  Basis-MelGAN: FV_FWD_BASIS_INFERENCE semantics only. */
+int fv_forward_ragged(fv_handle* h, const float* mel, int B, int T, const int32_t* lens_host, float* out, float* out2,
+                      void* workspace, size_t workspace_bytes, int flags, void* stream);
 /* Same as fv_forward, but brackets every learned layer with CUDA events on `stream` and reports, per layer
  * launch: which kernel ran (0 = fp32 CUDA-core conv, 1 = tcgen05 conv), its algorithmic FLOPs / bytes and its
  * device time.  Synchronises the stream.  bench.py uses it for the live roofline numbers. */

@@ -508,3 +508,38 @@ def test_publish_pattern_and_long_utterance(tmp_path, specs):
         ref = P.basis_melgan_inference(wt, cfg, torch.from_numpy(mel)).numpy()[:-15]
     assert est.shape[0] == ref.shape[0]
     assert np.abs(est.cpu().numpy() - (ref - want[: ref.shape[0]])).max() < TOL
+
+
+# ------------------------------------------------------------------------------------------ ragged batches
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("key", ["hifigan-light", "multiband-hifigan-light", "multiband-hifigan-large", "melgan-original",
+                                 "basis-melgan-light"])
+def test_ragged_batch_equals_per_utterance_inference(specs, key, tc):
+    """inference_batch([mel_0 .. mel_n]) (one launch chain over the padded batch, fv_forward_ragged) must give every
+    utterance what the reference's per-file loop gives it (bin/test.py:123-131): checked against this library's own
+    B=1 inference (same arithmetic, so <= a few ulp) and against the CPU port of the reference (<= 1e-4)."""
+    name, cfg = specs[key]["model_name"], specs[key]["config"]
+    m = make_model(specs, key, tc=tc)
+    lens = [57, 4, 131, 64, 9]                       # includes the MelGAN-family minimum (ReflectionPad1d(3) -> T >= 4)
+    mels = [synth_mel(1, T, seed=20 + i)[0].T.copy() for i, T in enumerate(lens)]     # (T, 80) like bin/synthesize.py
+    w = P.to_torch(folded_weights(specs, key))
+    with torch.no_grad():
+        got = m.inference_batch(mels)
+        assert len(got) == len(mels)
+        for i, mel in enumerate(mels):
+            single = m.inference(mel)
+            assert got[i].shape == single.shape, (i, got[i].shape, single.shape)
+            # the tile planner may chunk K differently for (B=5, T=131) and (B=1, T=lens[i]): summation order, not semantics
+            assert (got[i] - single).abs().max().item() < (2e-5 if tc else 2e-6), \
+                f"utterance {i} (T={lens[i]}) differs from B=1 inference"
+            want = P.inference(name, w, cfg, torch.from_numpy(mel)).reshape(-1).numpy()
+            assert np.abs(got[i].cpu().numpy() - want).max() < TOL
+
+
+def test_ragged_batch_rejects_bad_lengths(specs):
+    m = make_model(specs, "melgan-original")
+    with pytest.raises(_lib.FvError, match="out of range"):
+        m.inference_batch([np.zeros((3, 80), np.float32), np.zeros((10, 80), np.float32)])    # 3 < ReflectionPad minimum
+    with pytest.raises(RuntimeError, match="expected"):
+        m.inference_batch([np.zeros((10, 79), np.float32)])
+    assert m.inference_batch([]) == []
