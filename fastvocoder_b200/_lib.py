@@ -47,7 +47,10 @@ class FvConfig(C.Structure):
         ("basis_L", C.c_int32),
         ("pqmf_subbands", C.c_int32),
         ("pqmf_taps", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("upsample_layer", C.c_int32),
+        ("use_causal_conv", C.c_int32),
+        ("lastlinear", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

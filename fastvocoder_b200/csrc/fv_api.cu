@@ -75,6 +75,8 @@ static int derive_layer(const Layer& l, const float* w_canon, float* wd, cudaStr
   const int g = grid_for(n);
   if (l.type == L_CONV) derive_conv_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cout, l.Cin, l.K);
   else if (l.type == L_CONVT) derive_convt_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cin, l.Cout, l.K, l.stride, l.Kd);
+  else if (l.type == L_UPCONV)
+    derive_upconv_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cin, l.Cout, l.K, l.stride, l.padding, l.dmin, l.Kd);
   else derive_basis_kernel<<<g, 256, 0, st>>>(w_canon, wd, l.Cout, l.Cin);
   g_launches++;
   FV_CUDA(cudaGetLastError());
@@ -102,7 +104,7 @@ struct LayerCall {
 
 static long long layer_out_len(const Layer& l, long long Lin) {
   if (l.type == L_CONV || l.type == L_PAIR) return Lin;
-  if (l.type == L_CONVT) return Model::convt_out_len(l, Lin);
+  if (l.type == L_CONVT || l.type == L_UPCONV) return Model::convt_out_len(l, Lin);
   return (Lin + 1) * l.N;  // basis: samples
 }
 
@@ -119,7 +121,8 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   long long out_per_b;
   if (l.type == L_CONV) {
     a.Lpos = (int)c.Lin;
-    a.pad_left = (l.K - 1) * l.dil / 2;  // get_padding (modules.py:186) == ReflectionPad1d((k-1)//2*d)
+    // get_padding (modules.py:186) == ReflectionPad1d((k-1)//2*d); CausalConv1d: everything on the left (modules.py:282,297)
+    a.pad_left = l.causal ? (l.K - 1) * l.dil : (l.K - 1) * l.dil / 2;
     a.out_layout = OUT_BCL;
     a.bias_mod = l.Cout;
     out_per_b = (long long)l.Cout * c.Lin;
@@ -141,6 +144,14 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
     a.pad_left = l.Kd - 1;
     a.out_layout = OUT_PHASE;
     a.ph_stride = l.stride; a.ph_pad = l.padding; a.ph_cout = l.Cout; a.ph_lout = (int)Lout;
+    a.bias_mod = l.Cout;
+    out_per_b = (long long)l.Cout * Lout;
+  } else if (l.type == L_UPCONV) {   // nearest stretch + conv, polyphase: t = pos*u + r, taps at x[pos + dmin + jj]
+    const long long Lout = Model::convt_out_len(l, c.Lin);
+    a.Lpos = (int)((Lout + l.stride - 1) / l.stride);
+    a.pad_left = -l.dmin;
+    a.out_layout = OUT_PHASE;
+    a.ph_stride = l.stride; a.ph_pad = 0; a.ph_cout = l.Cout; a.ph_lout = (int)Lout;
     a.bias_mod = l.Cout;
     out_per_b = (long long)l.Cout * Lout;
   } else {
@@ -185,6 +196,8 @@ static size_t max_act_floats(const Model& m, int B, int T) {
   }
   if (m.basis >= 0) {
     size_t v = (size_t)B * (size_t)((m.len_after(T, (int)m.stages.size() - 1) + 1) * (m.cfg.basis_L / 2));
+    if (v > mx) mx = v;
+    v = (size_t)B * m.cfg.out_channels * (size_t)m.len_after(T, (int)m.stages.size() - 1);   // LastLinear output
     if (v > mx) mx = v;
   }
   return (mx + 63) / 64 * 64;
@@ -425,6 +438,14 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     lc.post_tanh = c.use_final_activation ? 1 : 0;
     if ((rc = call(m.post, lc))) return rc;
   } else {  // ReLU -> Linear(C->L) -> overlap_and_add(L/2)  (basis_melgan.py:121, modules.py:264-267)
+    if (m.ll1 >= 0) {   // LastLinear (modules.py:124-131), eval-mode BatchNorm folded into the two 1x1 convs
+      LayerCall l1;
+      l1.x = cur; l1.y = other; l1.B = Be; l1.Lin = L; l1.pre_slope = 0.2f; l1.lens = lens_at((int)m.stages.size() - 1, 0);
+      if ((rc = call(m.ll1, l1))) return rc;
+      LayerCall l2 = l1;
+      l2.x = other; l2.y = cur;
+      if ((rc = call(m.ll2, l2))) return rc;
+    }
     const Layer& bl = m.layers[m.basis];
     const long long full_len = (L + 1) * bl.N;
     LayerCall lc;

@@ -368,6 +368,26 @@ __global__ void derive_convt_kernel(const float* __restrict__ w, float* __restri
     wd[i] = kk < K ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
   }
 }
+// UpsampleLayer conv [Cout][Cin][K] -> [Cin][Kd][u*Cout]: taps hitting the same input sample are summed (in double)
+__global__ void derive_upconv_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cin, int Cout, int K, int u,
+                                     int pad, int dmin, int Kd) {
+  const int N = u * Cout;
+  const long long n = (long long)Cin * Kd * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int nn = (int)(i % N);
+    const long long q = i / N;
+    const int jj = (int)(q % Kd);
+    const int ci = (int)(q / Kd);
+    const int r = nn / Cout, co = nn - r * Cout;
+    double acc = 0.0;
+    for (int j = 0; j < K; ++j) {
+      const int v = r - pad + j;
+      const int d = v >= 0 ? v / u : -((-v + u - 1) / u);   // floor division
+      if (d == dmin + jj) acc += (double)w[((long long)co * Cin + ci) * K + j];
+    }
+    wd[i] = (float)acc;
+  }
+}
 // Pair of 1x1 convs (ResidualStack stack.4 + skip_layer): [C][C][1] x2 -> [2C][1][C] and summed bias
 __global__ void derive_pair_kernel(const float* __restrict__ wa, const float* __restrict__ wb, const float* __restrict__ ba,
                                    const float* __restrict__ bb, float* __restrict__ wd, float* __restrict__ bias, int C) {

@@ -28,7 +28,7 @@ struct Param {
   }
 };
 
-enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2, L_PAIR = 3 };
+enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2, L_PAIR = 3, L_UPCONV = 4 };
 
 // One learned layer as the kernels see it (a stride-1 "GEMM conv" over time):
 //   y[n, pos] = bias[n % bias_mod] + sum_{ci, j} Wd[ci][j][n] * act(x)[ci, pos - pad_left + j*dil]
@@ -36,12 +36,18 @@ enum LayerType { L_CONV = 0, L_CONVT = 1, L_BASIS = 2, L_PAIR = 3 };
 // ConvTranspose1d (polyphase): N = stride*Cout (n = r*Cout + co), Kd = ceil(K/stride),
 //               positions i' = (t+p)/stride, output sample t = i'*stride + r - p
 // Basis linear + overlap-add (L = 2*hop): N = hop, Kd = 2, positions = frames+1, output time-major
+// UpsampleLayer (nearest stretch by u, then Conv1d(k, padding p), modules.py:160-177) in polyphase form: output sample
+//               t = pos*u + r reads xu[t - p + j] = x[pos + floor((r - p + j)/u)], so N = u*Cout (n = r*Cout + co), the
+//               taps that land on the same input sample are pre-summed:  Wd[ci][jj][n] = sum_{j: floor((r-p+j)/u) = dmin+jj} w[co][ci][j],
+//               dmin = floor(-p/u), Kd = floor((u-1-p+k-1)/u) - dmin + 1, pad_left = -dmin
 struct Layer {
   LayerType type = L_CONV;
   int w_param = -1, b_param = -1;
   int w_param2 = -1, b_param2 = -1;  // L_PAIR: second 1x1 conv (the skip layer) fused along the input-channel axis
   int Cin = 0, Cout = 0, K = 0, dil = 1;
-  int stride = 1, padding = 0, output_padding = 0;  // ConvTranspose1d
+  int stride = 1, padding = 0, output_padding = 0;  // ConvTranspose1d; UpsampleLayer: stride = stretch u, padding = conv padding
+  int dmin = 0;                                     // UpsampleLayer: smallest input offset (<= 0)
+  bool causal = false;                              // CausalConv1d: all (K-1)*dil samples of padding on the left
   // derived GEMM view
   int N = 0, Kd = 0;
   int64_t wd_offset = 0;  // float offset of the [Cin][Kd][N] image in the derived buffer
@@ -73,6 +79,7 @@ struct Model {
   std::vector<Layer> layers;
   int64_t derived_floats = 0;
   int pre = -1, post = -1, basis = -1;
+  int ll1 = -1, ll2 = -1;   // Basis-MelGAN LastLinear (BatchNorm folded on the host): two 1x1 convs after the last stage
   std::vector<Stage> stages;
   std::string err;
 
@@ -127,7 +134,22 @@ struct Model {
     return (int)layers.size() - 1;
   }
 
+  static int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+  int add_upconv(const std::string& prefix, int Cin, int Cout, int K, int u, int pad, bool bias) {
+    Layer l;
+    l.type = L_UPCONV;
+    l.Cin = Cin; l.Cout = Cout; l.K = K; l.dil = 1;
+    l.stride = u; l.padding = pad;
+    if (bias) l.b_param = add_param(prefix + ".conv.bias", {Cout});
+    l.w_param = add_param(prefix + ".conv.weight", {Cout, Cin, K});
+    l.N = u * Cout;
+    l.dmin = floor_div(-pad, u);
+    l.Kd = floor_div(u - 1 - pad + K - 1, u) - l.dmin + 1;
+    return push_layer(l);
+  }
+  // output length of an upsampling layer (ConvTranspose1d or UpsampleLayer)
   static int64_t convt_out_len(const Layer& l, int64_t Lin) {
+    if (l.type == L_UPCONV) return Lin * l.stride + 2 * l.padding - l.K + 1;
     return (Lin - 1) * l.stride - 2 * l.padding + l.K + l.output_padding;
   }
   // time length after stage s (s = -1: after conv_pre)
@@ -148,9 +170,12 @@ struct Model {
       if (c.channels[i] <= 0) return fail("channels[] must be > 0");
     for (int i = 0; i < c.num_upsamples; ++i) {
       if (c.upsample_rates[i] <= 0 || c.upsample_kernel_sizes[i] <= 0) return fail("bad upsample rate/kernel");
-      if (c.upsample_kernel_sizes[i] < c.upsample_rates[i]) return fail("upsample kernel < rate unsupported");
+      if (!c.upsample_layer && c.upsample_kernel_sizes[i] < c.upsample_rates[i]) return fail("upsample kernel < rate unsupported");
     }
     if (c.pre_kernel_size <= 0 || c.pre_kernel_size % 2 == 0) return fail("Not support even number kernel size.");
+    if (c.use_causal_conv && is_hifi()) return fail("use_causal_conv is a MelGAN-family switch");
+    if (c.lastlinear && c.kind != FV_BASIS_MELGAN) return fail("lastlinear is a BasisMelGANGenerator option (basis_melgan.py:38)");
+    if (c.upsample_layer && c.kind == FV_MELGAN) return fail("transposedconv=False is not a MelGANGenerator option (melgan.py:20-36)");
     const bool bias = c.bias != 0;
     if (is_hifi()) {
       if (c.num_kernels <= 0 || c.num_kernels > FV_MAX_BRANCH) return fail("num_kernels out of range");
@@ -161,8 +186,12 @@ struct Model {
       std::vector<int> ups;
       for (int i = 0; i < c.num_upsamples; ++i) {
         snprintf(buf, sizeof buf, "ups.%d", i);
-        ups.push_back(add_convt(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i],
-                                c.upsample_rates[i], bias));
+        if (c.upsample_layer)   // hifigan.py:32-38: UpsampleLayer(.., upsample_rate=u, kernel_size=k, stride=1, padding=k//2)
+          ups.push_back(add_upconv(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i], c.upsample_rates[i],
+                                   c.upsample_kernel_sizes[i] / 2, bias));
+        else
+          ups.push_back(add_convt(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i],
+                                  c.upsample_rates[i], bias));
       }
       for (int i = 0; i < c.num_upsamples; ++i) {
         Stage st;
@@ -203,7 +232,7 @@ struct Model {
         if (c.pqmf_taps <= 0 || c.pqmf_taps % 2) return fail("The number of taps mush be even number.");
       }
     } else {
-      if (c.stacks < 0 || c.stack_kernel_size <= 0 || (c.stack_kernel_size - 1) % 2 != 0)
+      if (c.stacks < 0 || c.stack_kernel_size <= 0 || (!c.use_causal_conv && (c.stack_kernel_size - 1) % 2 != 0))
         return fail("Not support even number kernel size.");
       int idx = 1;
       snprintf(buf, sizeof buf, "melgan.%d", idx);
@@ -213,16 +242,23 @@ struct Model {
         Stage st;
         st.Cout = c.channels[i + 1];
         snprintf(buf, sizeof buf, "melgan.%d", idx + 1);
-        st.up = add_convt(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i],
-                          c.upsample_rates[i], true);
+        if (c.upsample_layer)   // basis_melgan.py:82-88: UpsampleLayer(.., kernel_size=2*scale+1, stride=1, padding=scale)
+          st.up = add_upconv(buf, c.channels[i], c.channels[i + 1], 2 * c.upsample_rates[i] + 1, c.upsample_rates[i],
+                             c.upsample_rates[i], true);
+        else
+          st.up = add_convt(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i],
+                            c.upsample_rates[i], true);
         idx += 2;
         int dil = 1;
         for (int j = 0; j < c.stacks; ++j) {
           Stack sk;
           sk.dilation = dil;
-          snprintf(buf, sizeof buf, "melgan.%d.stack.2", idx);
+          // non-causal: stack = [act, pad, conv, act, conv1x1] -> stack.2 / stack.4;  causal: [act, CausalConv1d, act,
+          // conv1x1] -> stack.1.conv / stack.3 (modules.py:345-361)
+          snprintf(buf, sizeof buf, c.use_causal_conv ? "melgan.%d.stack.1.conv" : "melgan.%d.stack.2", idx);
           sk.dil_conv = add_conv(buf, st.Cout, st.Cout, c.stack_kernel_size, dil, true);
-          snprintf(buf, sizeof buf, "melgan.%d.stack.4", idx);
+          layers[sk.dil_conv].causal = c.use_causal_conv != 0;
+          snprintf(buf, sizeof buf, c.use_causal_conv ? "melgan.%d.stack.3" : "melgan.%d.stack.4", idx);
           sk.conv1x1 = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
           snprintf(buf, sizeof buf, "melgan.%d.skip_layer", idx);
           sk.skip = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
@@ -250,8 +286,17 @@ struct Model {
         post = add_conv(buf, c.channels[c.num_upsamples], c.out_channels, c.post_kernel_size, 1, true);
       } else {
         if (c.basis_L <= 0 || c.basis_L % 2) return fail("basis L must be even (hop = L/2)");
-        if (c.out_channels != c.channels[c.num_upsamples]) return fail("basis out_channels != channels[-1]");
-        basis = add_basis("basis_signal.layer.weight", c.channels[c.num_upsamples], c.basis_L);
+        const int Cl = c.channels[c.num_upsamples];
+        if (c.lastlinear) {   // basis_melgan.py:117-118, modules.py:116-132
+          if (c.out_channels <= 0) return fail("out_channels must be > 0");
+          snprintf(buf, sizeof buf, "melgan.%d.linear_1", idx);
+          ll1 = add_conv(buf, Cl, Cl, 1, 1, true);
+          snprintf(buf, sizeof buf, "melgan.%d.linear_2", idx);
+          ll2 = add_conv(buf, Cl, c.out_channels, 1, 1, true);
+        } else if (c.out_channels != Cl) {
+          return fail("basis out_channels != channels[-1]");
+        }
+        basis = add_basis("basis_signal.layer.weight", c.out_channels, c.basis_L);
       }
     }
     return true;
@@ -275,8 +320,10 @@ struct Model {
     double L = T;
     for (size_t s = 0; s < stages.size(); ++s) {
       const Layer& up = layers[stages[s].up];
-      m += (double)up.Cin * up.Cout * up.K * L;  // every input sample meets every tap
-      L = (double)convt_out_len(up, (int64_t)L);
+      const double Lup = (double)convt_out_len(up, (int64_t)L);
+      // ConvTranspose1d: every input sample meets every tap; UpsampleLayer: a dense conv on the stretched signal
+      m += (double)up.Cin * up.Cout * up.K * (up.type == L_UPCONV ? Lup : L);
+      L = Lup;
       for (auto& br : stages[s].branches)
         for (auto& u : br.units) {
           m += conv(layers[u.c1], L);
@@ -286,6 +333,7 @@ struct Model {
         m += conv(layers[sk.dil_conv], L) + conv(layers[sk.conv1x1], L) + conv(layers[sk.skip], L);
     }
     if (post >= 0) m += conv(layers[post], L);
+    if (ll1 >= 0) m += conv(layers[ll1], L) + conv(layers[ll2], L);
     if (basis >= 0) m += (double)layers[basis].Cin * layers[basis].Cout * L;
     return m;
   }

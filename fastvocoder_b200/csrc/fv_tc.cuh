@@ -269,7 +269,7 @@ struct TcWeights {
       // zero-padded output columns, never stored: Basis hop (15) and the narrow output convs (conv_post 1 / 4 channels)
       if ((l.type == L_BASIS || (l.type == L_CONV && l.N < 16)) && l.N % 16) npad = (l.N + 15) / 16 * 16;
       int nt = (l.Cin % 16 == 0) ? tc_pick_nt(npad) : 0;
-      if (l.type == L_CONVT && l.Cout % 16) nt = 0;  // a 16-column epilogue chunk must stay inside one phase
+      if ((l.type == L_CONVT || l.type == L_UPCONV) && l.Cout % 16) nt = 0;  // a 16-column epilogue chunk must stay inside one phase
       if (nt == 0) continue;
       t.eligible = true;
       t.NT = nt;

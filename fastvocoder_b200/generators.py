@@ -302,11 +302,10 @@ class _NativeGenerator(torch.nn.Module):
 
 def _fill_hifi(cfg, kind, resblock_kernel_sizes, upsample_rates, upsample_initial_channel, resblock_type,
                upsample_kernel_sizes, resblock_dilation_sizes, transposedconv, bias, out_channels):
-    if transposedconv is False:
-        raise NotImplementedError("transposedconv=False (UpsampleLayer, modules.py:160-177) is not on the "
-                                  "B200 path yet; every shipped config uses ConvTranspose1d")
     cfg.kind = kind
     cfg.in_channels = 80
+    # hifigan.py:31-46: `transposedconv == False` -> UpsampleLayer (nearest stretch + Conv1d(k, padding k//2))
+    cfg.upsample_layer = 1 if transposedconv == False else 0   # noqa: E712  (the reference's own comparison)
     cfg.bias = 1 if bias else 0
     cfg.num_upsamples = len(upsample_rates)
     if len(upsample_kernel_sizes) != len(upsample_rates):
@@ -402,12 +401,14 @@ class MultiBandHiFiGANGenerator(_NativeGenerator):
 def _fill_melgan(cfg, kind, in_channels, out_channels, kernel_size, channels, upsample_scales, stack_kernel_size,
                  stacks, use_final_nonlinear_activation, use_causal_conv, nonlinear_activation,
                  nonlinear_activation_params, pad):
-    if use_causal_conv:
-        raise NotImplementedError("use_causal_conv=True (modules.py:273-317) is not on the B200 path; "
-                                  "every shipped config sets it False")
     if nonlinear_activation != "LeakyReLU" or pad != "ReflectionPad1d":
         raise NotImplementedError("only LeakyReLU + ReflectionPad1d (the shipped configs) are implemented")
-    assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."
+    if not use_causal_conv:
+        assert (kernel_size - 1) % 2 == 0, "Not support even number kernel size."   # melgan.py:63-64
+    elif (kernel_size - 1) % 2 != 0:
+        raise NotImplementedError("use_causal_conv with an even kernel_size changes the sequence length in the "
+                                  "first / last layer (melgan.py:68-71); not wired")
+    cfg.use_causal_conv = 1 if use_causal_conv else 0
     if len(channels) != len(upsample_scales) + 1:
         raise ValueError("channels must have len(upsample_scales) + 1 entries")
     slope = float(nonlinear_activation_params.get("negative_slope", 0.01))
@@ -477,21 +478,101 @@ class BasisMelGANGenerator(_NativeGenerator):
                  use_causal_conv=False, transposedconv=True, lastlinear=False):
         if not bias:
             raise NotImplementedError("bias=False Basis-MelGAN is not wired (no shipped config uses it)")
-        if transposedconv is False or lastlinear:
-            raise NotImplementedError("transposedconv=False / lastlinear=True are not on the B200 path "
-                                      "(no shipped config uses them)")
-        cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_BASIS_MELGAN, in_channels, channels[-1], kernel_size, channels,
+        # without LastLinear the predictor's width is channels[-1] (basis_melgan.py:70-121 never uses out_channels)
+        width = out_channels if lastlinear else channels[-1]
+        cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_BASIS_MELGAN, in_channels, width, kernel_size, channels,
                            upsample_scales, stack_kernel_size, stacks, use_final_nonlinear_activation,
                            use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad)
         cfg.basis_L = L
+        cfg.lastlinear = 1 if lastlinear else 0
+        # LastLinear (modules.py:116-132) sits at index 2 + sum(2 + stacks) of the nn.Sequential
+        self._ll = f"melgan.{2 + len(upsample_scales) * (2 + stacks)}" if lastlinear else None
+        self._ll_folded = False
+        # basis_melgan.py:82-99: `transposedconv == False` -> UpsampleLayer(k = 2*scale+1, padding = scale)
+        cfg.upsample_layer = 1 if transposedconv == False else 0   # noqa: E712
         bw = torch.as_tensor(basis_signal_weight).float()
-        if tuple(bw.shape) != (L, channels[-1]):
-            raise ValueError(f"basis_signal_weight must be [L={L}, {channels[-1]}], got {tuple(bw.shape)}")
+        if tuple(bw.shape) != (L, width):
+            raise ValueError(f"basis_signal_weight must be [L={L}, {width}], got {tuple(bw.shape)}")
         super().__init__(cfg, use_weight_norm=use_weight_norm)
+        if self._ll:   # fresh nn.BatchNorm1d state (identity up to eps)
+            self._bn = OrderedDict()
+            for q in ("bn_1", "bn_2"):
+                C_ = channels[-1]
+                self._bn[f"{self._ll}.{q}.weight"] = torch.ones(C_)
+                self._bn[f"{self._ll}.{q}.bias"] = torch.zeros(C_)
+                self._bn[f"{self._ll}.{q}.running_mean"] = torch.zeros(C_)
+                self._bn[f"{self._ll}.{q}.running_var"] = torch.ones(C_)
+                self._bn[f"{self._ll}.{q}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
         with torch.no_grad():
             self._view("basis_signal.layer.weight").copy_(bw)   # nn.Linear weight, no weight norm (modules.py:260-261)
         self.L = L
         self.pqmf = None
+
+    # ---- LastLinear: eval-mode BatchNorm1d folded into the 1x1 conv that follows it (host side, load time) ----------
+    _LL_NAMES = ("linear_1.weight", "linear_1.bias", "linear_2.weight", "linear_2.bias")
+
+    def _ll_unfold(self):
+        """Put the raw (checkpoint) linear_1/linear_2 parameters back into the packed buffer."""
+        if getattr(self, "_ll", None) and getattr(self, "_ll_folded", False):
+            with torch.no_grad():
+                for n in self._LL_NAMES:
+                    self._view(f"{self._ll}.{n}").copy_(self._ll_raw[n])
+            self._ll_folded = False
+
+    def _fold(self):
+        self._ll_unfold()
+        super()._fold()                       # weight norm first: g*v/||v|| -> raw .weight
+        if not getattr(self, "_ll", None) or not hasattr(self, "_bn"):
+            return
+        with torch.no_grad():
+            self._ll_raw = {n: self._view(f"{self._ll}.{n}").detach().cpu().clone() for n in self._LL_NAMES}
+            for q, lin in (("bn_1", "linear_1"), ("bn_2", "linear_2")):
+                g = self._bn[f"{self._ll}.{q}.weight"].double().cpu()
+                b = self._bn[f"{self._ll}.{q}.bias"].double().cpu()
+                mu = self._bn[f"{self._ll}.{q}.running_mean"].double().cpu()
+                var = self._bn[f"{self._ll}.{q}.running_var"].double().cpu()
+                a = g / torch.sqrt(var + 1e-5)                       # bn(x) = a*x + c   (eps = nn.BatchNorm1d default)
+                c = b - mu * a
+                W = self._ll_raw[f"{lin}.weight"].double()[:, :, 0]   # [Cout, Cin]
+                self._view(f"{self._ll}.{lin}.weight").copy_((W * a[None, :]).float().unsqueeze(-1))
+                self._view(f"{self._ll}.{lin}.bias").copy_((self._ll_raw[f"{lin}.bias"].double() + W @ c).float())
+        self._ll_folded = True
+        self._bound_key = None
+
+    def _reset_parameters(self):
+        if getattr(self, "_ll_folded", False):
+            self._ll_folded = False           # the views are about to be overwritten with fresh raw values
+        super()._reset_parameters()
+
+    def apply_weight_norm(self):
+        self._ll_unfold()
+        super().apply_weight_norm()
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        if getattr(self, "_ll", None):
+            self._ll_unfold()
+            state_dict = OrderedDict(state_dict)
+            missing_bn = []
+            for k in list(self._bn):
+                if k in state_dict:
+                    t = torch.as_tensor(state_dict.pop(k)).detach().cpu()
+                    self._bn[k] = t.clone() if k.endswith("num_batches_tracked") else t.float().clone()
+                elif not k.endswith("num_batches_tracked"):
+                    missing_bn.append(k)
+            if strict and missing_bn:
+                raise RuntimeError(f"Error(s) in loading state_dict for {type(self).__name__}: missing keys {missing_bn}")
+        return super().load_state_dict(state_dict, strict)
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        if getattr(self, "_ll", None):
+            if self._ll_folded:               # report checkpoint-form (un-folded) LastLinear parameters
+                for n in self._LL_NAMES:
+                    if f"{self._ll}.{n}" in sd:
+                        sd[f"{self._ll}.{n}"] = self._ll_raw[n].clone()
+            for k, v in self._bn.items():
+                sd[k] = v.clone()
+        return sd
 
     def forward(self, c, return_weight=True):
         """[B, 80, T] -> (est_source - zero_est [B, 16T*15], weight - zero_weight [B, 16T, C])
@@ -541,7 +622,8 @@ def build_generator(model_name: str, config: dict):
                                     stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
                                     use_weight_norm=config["use_weight_norm"],
                                     use_causal_conv=config["use_causal_conv"],
-                                    transposedconv=config["transposedconv"])
+                                    transposedconv=config["transposedconv"],
+                                    lastlinear=config.get("lastlinear", False))
     else:
         raise Exception("no model find!")
     return cls(resblock_kernel_sizes=config["resblock_kernel_sizes"], upsample_rates=config["upsample_rates"],

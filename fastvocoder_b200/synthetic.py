@@ -28,13 +28,15 @@ def _is_conv_transpose(name: str) -> bool:
     return bool(m) and int(m.group(1)) != 1
 
 
-def _gain(name: str) -> float:
+def _gain(name: str, shape=()) -> float:
     """Per-layer gain (found empirically so that the four shipped configs stay O(1))."""
+    if ".conv.weight" in name and len(shape) == 3 and shape[0] > 4 and ".stack." not in name:
+        return 1.3                                                    # UpsampleLayer's conv (modules.py:173)
     if name.startswith("conv_post"):                                  # last conv -> pre-tanh scale
         return 1.0
     if ".conv.weight" in name:                                        # MelGAN LastLayer
         return 0.5
-    if ".convs2." in name:                                            # residual branch output
+    if ".convs2." in name or ".convs." in name:                       # residual branch output (ResBlock1 / ResBlock2)
         return 0.5
     if ".stack.4." in name:
         return 0.8
@@ -49,6 +51,12 @@ def synth_param(name: str, shape, seed: int) -> np.ndarray:
     """One tensor, keyed by (seed, name) so that specs may be generated in any order."""
     rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
     shape = tuple(int(s) for s in shape)
+    if ".bn_" in name:                                                # LastLinear's BatchNorm1d (modules.py:120-122)
+        if name.endswith("running_var"):
+            return rng.uniform(0.5, 1.5, shape).astype(np.float32)
+        if name.endswith("running_mean") or name.endswith(".bias"):
+            return (rng.standard_normal(shape) * 0.1).astype(np.float32)
+        return (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)   # affine weight
     if name.endswith(".bias"):
         return (rng.standard_normal(shape) * 0.05).astype(np.float32)
     if len(shape) == 3:
@@ -60,7 +68,7 @@ def synth_param(name: str, shape, seed: int) -> np.ndarray:
         fan_in = shape[1]
     else:
         fan_in = 1
-    std = _gain(name) / np.sqrt(fan_in)
+    std = _gain(name, shape) / np.sqrt(fan_in)
     return (rng.standard_normal(shape) * std).astype(np.float32)
 
 

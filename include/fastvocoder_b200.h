@@ -82,7 +82,19 @@ typedef struct fv_config {
   /* PQMF (pqmf.py:61): only used by FV_MB_HIFIGAN */
   int32_t pqmf_subbands;                /* 4 */
   int32_t pqmf_taps;                    /* 62 */
-  int32_t reserved[8];
+  /* non-default architecture switches (YAML keys no shipped config turns on) */
+  int32_t upsample_layer;               /* 1: `transposedconv: False` -> UpsampleLayer = nearest-neighbour stretch + Conv1d
+                                           (modules.py:160-177; HiFi: k = upsample_kernel_sizes[i], padding k/2,
+                                           hifigan.py:32-38; Basis: k = 2*scale+1, padding scale, basis_melgan.py:82-88) */
+  int32_t use_causal_conv;              /* 1: MelGAN family `use_causal_conv: True` -> the ResidualStack's dilated conv is
+                                           CausalConv1d (modules.py:273-297, 355-361): (k-1)*d samples of padding on the
+                                           LEFT only (reflected, the stack's `pad` class) */
+  int32_t lastlinear;                   /* 1: Basis-MelGAN `lastlinear: True` -> LastLinear after the last stage
+                                           (modules.py:116-132, basis_melgan.py:117-118): LReLU.2 -> BN -> 1x1(C->C) ->
+                                           LReLU.2 -> BN -> 1x1(C->out_channels).  Inference (eval-mode) semantics: the
+                                           host folds each BatchNorm1d's running statistics into the 1x1 conv that follows
+                                           it, so the packed `melgan.N.linear_{1,2}.{weight,bias}` are the folded ones */
+  int32_t reserved[5];
 } fv_config;
 
 typedef struct fv_handle fv_handle;

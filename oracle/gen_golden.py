@@ -87,6 +87,89 @@ def build(model_name, config):
                transposedconv=config["transposedconv"], bias=config["bias"])
 
 
+# Non-default architecture switches: YAML keys the reference classes accept but no shipped conf
+# turns on.  Built by calling the reference constructors directly with the shipped light config + the override.
+VARIANTS = {
+    # key: (model_name, base yaml, overrides, (B, T))
+    "hifigan-light-upsamplelayer": ("hifigan", "conf/hifigan/light.yaml", {"transposedconv": False}, (2, 24)),
+    "hifigan-light-resblock2": ("hifigan", "conf/hifigan/light.yaml",
+                                {"resblock_type": "2", "resblock_dilation_sizes": [[1, 3], [1, 3], [1, 3]]}, (2, 24)),
+    "multiband-hifigan-light-upsamplelayer": ("multiband-hifigan", "conf/multiband-hifigan/light.yaml",
+                                              {"transposedconv": False}, (2, 24)),
+    "melgan-causal": ("melgan", "conf/melgan/original.yaml", {"use_causal_conv": True}, (2, 12)),
+    "basis-melgan-upsamplelayer": ("basis-melgan", "conf/basis-melgan/light.yaml", {"transposedconv": False}, (2, 24)),
+    "basis-melgan-causal-lastlinear": ("basis-melgan", "conf/basis-melgan/light.yaml",
+                                       {"use_causal_conv": True, "lastlinear": True, "out_channels": 128}, (2, 24)),
+}
+
+
+def build_variant(model_name, config):
+    if model_name == "basis-melgan":    # bin/synthesize.py never passes `lastlinear`; the class does (basis_melgan.py:41)
+        return BasisMelGANGenerator(basis_signal_weight=torch.zeros(config["L"], config["out_channels"]).float(),
+                                    L=config["L"], in_channels=config["in_channels"],
+                                    out_channels=config["out_channels"], kernel_size=config["kernel_size"],
+                                    channels=config["channels"], upsample_scales=config["upsample_scales"],
+                                    stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
+                                    use_weight_norm=config["use_weight_norm"],
+                                    use_causal_conv=config["use_causal_conv"],
+                                    transposedconv=config["transposedconv"],
+                                    lastlinear=config.get("lastlinear", False))
+    return build(model_name, config)
+
+
+def run_model_golden(key, model_name, config, B, T, specs, manifest, builder, realmel):
+    torch.manual_seed(0)
+    model = builder(model_name, config)
+    wn_sd = model.state_dict()                       # weight-norm form (checkpoint form)
+    model.eval()
+    model.remove_weight_norm()                       # bin/synthesize.py:69-71
+    folded_sd = model.state_dict()
+    specs[key] = {"model_name": model_name, "config": config, "spec_wn": spec_of(wn_sd),
+                  "spec_folded": spec_of(folded_sd)}
+    spec = [(k, tuple(v.shape)) for k, v in folded_sd.items()
+            if not k.startswith("pqmf.") and not k.endswith("num_batches_tracked")]
+    weights = synth_state_dict(spec, seed=0)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=False)
+    mel = synth_mel(B, T, seed=1)
+    x32 = torch.from_numpy(mel)
+    arrays = {"mel": mel}
+    with torch.no_grad():
+        y32 = np_out(model(x32))
+        inf32 = np_out(model.inference(mel[0].T.copy()))
+        m64 = model.double()
+        y64 = np_out(m64(x32.double()))
+        inf64 = np_out(m64.inference(torch.from_numpy(mel[0].T.copy()).double()))
+        model.float()
+    for i, (a, b) in enumerate(zip(y32, y64)):
+        arrays[f"forward{i}_f32"] = a
+        if i == 0:
+            arrays[f"forward{i}_f64"] = b
+    arrays["inference_f32"] = inf32[0]
+    arrays["inference_f64"] = inf64[0]
+    print(key, "forward", [a.shape for a in y32], "peak", [float(np.abs(a).max()) for a in y32],
+          "fp32-vs-fp64", [float(np.abs(a - b).max()) for a, b in zip(y32, y64)], "inference", inf32[0].shape)
+    np.savez_compressed(os.path.join(OUT, f"model_{key}.npz"), **arrays)
+    manifest[key] = {k: list(v.shape) for k, v in arrays.items()}
+
+
+def variants_main():
+    """Add the VARIANTS goldens to an existing tests/golden (does not touch the shipped-config fixtures)."""
+    with open(os.path.join(OUT, "specs.json")) as f:
+        specs = json.load(f)
+    with open(os.path.join(OUT, "manifest.json")) as f:
+        manifest = json.load(f)
+    for key, (model_name, ypath, over, (B, T)) in VARIANTS.items():
+        with open(os.path.join(REF, ypath)) as f:
+            config = yaml.load(f, Loader=yaml.Loader)
+        config.update(over)
+        run_model_golden(key, model_name, config, B, T, specs, manifest, build_variant, False)
+    with open(os.path.join(OUT, "specs.json"), "w") as f:
+        json.dump(specs, f, indent=0, sort_keys=True)
+    with open(os.path.join(OUT, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    print("wrote variants into", OUT)
+
+
 def spec_of(sd):
     return [[k, list(v.shape)] for k, v in sd.items()]
 
@@ -289,4 +372,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--variants" in sys.argv:
+        variants_main()
+    else:
+        main()
+        variants_main()

@@ -121,16 +121,57 @@ def resblock2(x, params, prefix, kernel_size, dilations):
     return x
 
 
-def residual_stack(c, params, prefix, kernel_size, dilation, slope=0.2):
-    """ResidualStack.forward (non-causal), modules.py:353-382:
-    stack = LReLU -> ReflectionPad1d((k-1)//2*d) -> Conv1d(k, dil d) -> LReLU -> Conv1d 1x1; + skip_layer(c)."""
+def upsample_layer(x, w, b, upsample_rate, padding):
+    """UpsampleLayer.forward, modules.py:160-177: Stretch2d(nearest, x_scale = rate) on the time axis, then
+    Conv1d(kernel k, stride 1, zero padding `padding`).  F.interpolate(mode="nearest") with an integer scale
+    repeats every sample `rate` times: xu[t] = x[t // rate]."""
+    return conv1d(np.repeat(x, upsample_rate, axis=-1), w, b, padding=padding)
+
+
+def causal_conv1d(x, w, b, dilation, pad="reflect"):
+    """CausalConv1d.forward, modules.py:273-297: pad((k-1)*d) on BOTH sides with the stack's pad class
+    (ReflectionPad1d in every config), Conv1d(dilation d), then keep the first T outputs -> only the left
+    padding is ever read."""
+    K = w.shape[-1]
+    p = (K - 1) * dilation
+    xp = reflection_pad1d(x, p) if pad == "reflect" else np.pad(x, ((0, 0), (0, 0), (p, p)))
+    return conv1d(xp, w, b, dilation=dilation)[:, :, : x.shape[-1]]
+
+
+def residual_stack(c, params, prefix, kernel_size, dilation, slope=0.2, use_causal_conv=False):
+    """ResidualStack.forward, modules.py:343-382.  Non-causal:
+    stack = LReLU -> ReflectionPad1d((k-1)//2*d) -> Conv1d(k, dil d) -> LReLU -> Conv1d 1x1; + skip_layer(c).
+    Causal (modules.py:355-361): stack = LReLU -> CausalConv1d -> LReLU -> Conv1d 1x1 (keys stack.1.conv / stack.3)."""
     h = leaky_relu(c, slope)
-    h = reflection_pad1d(h, (kernel_size - 1) // 2 * dilation)
-    h = conv1d(h, params[f"{prefix}.stack.2.weight"], params[f"{prefix}.stack.2.bias"], dilation=dilation)
-    h = leaky_relu(h, slope)
-    h = conv1d(h, params[f"{prefix}.stack.4.weight"], params[f"{prefix}.stack.4.bias"])
+    if use_causal_conv:
+        h = causal_conv1d(h, params[f"{prefix}.stack.1.conv.weight"], params[f"{prefix}.stack.1.conv.bias"], dilation)
+        h = leaky_relu(h, slope)
+        h = conv1d(h, params[f"{prefix}.stack.3.weight"], params[f"{prefix}.stack.3.bias"])
+    else:
+        h = reflection_pad1d(h, (kernel_size - 1) // 2 * dilation)
+        h = conv1d(h, params[f"{prefix}.stack.2.weight"], params[f"{prefix}.stack.2.bias"], dilation=dilation)
+        h = leaky_relu(h, slope)
+        h = conv1d(h, params[f"{prefix}.stack.4.weight"], params[f"{prefix}.stack.4.bias"])
     s = conv1d(c, params[f"{prefix}.skip_layer.weight"], params[f"{prefix}.skip_layer.bias"])
     return h + s
+
+
+def batch_norm1d_eval(x, params, prefix, eps=1e-5):
+    """nn.BatchNorm1d in eval mode: (x - running_mean) / sqrt(running_var + eps) * weight + bias per channel."""
+    inv = 1.0 / np.sqrt(params[f"{prefix}.running_var"].astype(x.dtype) + np.asarray(eps, dtype=x.dtype))
+    return ((x - params[f"{prefix}.running_mean"].astype(x.dtype)[None, :, None]) * inv[None, :, None]
+            * params[f"{prefix}.weight"].astype(x.dtype)[None, :, None]
+            + params[f"{prefix}.bias"].astype(x.dtype)[None, :, None])
+
+
+def last_linear(x, params, prefix, slope=0.2):
+    """LastLinear.forward (eval mode), modules.py:116-132: LReLU -> BN -> 1x1 -> LReLU -> BN -> 1x1."""
+    x = leaky_relu(x, slope)
+    x = batch_norm1d_eval(x, params, f"{prefix}.bn_1")
+    x = conv1d(x, params[f"{prefix}.linear_1.weight"], params.get(f"{prefix}.linear_1.bias"))
+    x = leaky_relu(x, slope)
+    x = batch_norm1d_eval(x, params, f"{prefix}.bn_2")
+    return conv1d(x, params[f"{prefix}.linear_2.weight"], params.get(f"{prefix}.linear_2.bias"))
 
 
 def last_layer(x, params, prefix, kernel_size, slope=0.2):
@@ -237,8 +278,11 @@ def _hifigan_trunk(params, cfg, x):
     x = conv1d(x, params["conv_pre.weight"], params.get("conv_pre.bias"), padding=3)
     for i, (u, k) in enumerate(zip(rates, ksz)):
         x = leaky_relu(x, LRELU_SLOPE)
-        x = conv_transpose1d(x, params[f"ups.{i}.weight"], params.get(f"ups.{i}.bias"),
-                             stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
+        if cfg.get("transposedconv", True) == False:   # noqa: E712  hifigan.py:31-38
+            x = upsample_layer(x, params[f"ups.{i}.conv.weight"], params.get(f"ups.{i}.conv.bias"), u, k // 2)
+        else:
+            x = conv_transpose1d(x, params[f"ups.{i}.weight"], params.get(f"ups.{i}.bias"),
+                                 stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
         xs = None
         for j in range(num_kernels):
             r = rb(x, params, f"resblocks.{i * num_kernels + j}", rks[j], rds[j])
@@ -282,11 +326,16 @@ def _melgan_body(params, cfg, c, n_prefix="melgan"):
     idx = 2
     for i, u in enumerate(scales):
         x = leaky_relu(x, 0.2)                                                  # idx
-        x = conv_transpose1d(x, params[f"{n_prefix}.{idx + 1}.weight"], params.get(f"{n_prefix}.{idx + 1}.bias"),
-                             stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
+        if cfg.get("transposedconv", True) == False and "L" in cfg:   # noqa: E712  basis_melgan.py:82-88 only
+            x = upsample_layer(x, params[f"{n_prefix}.{idx + 1}.conv.weight"],
+                               params.get(f"{n_prefix}.{idx + 1}.conv.bias"), u, u)
+        else:
+            x = conv_transpose1d(x, params[f"{n_prefix}.{idx + 1}.weight"], params.get(f"{n_prefix}.{idx + 1}.bias"),
+                                 stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
         idx += 2
         for j in range(stacks):
-            x = residual_stack(x, params, f"{n_prefix}.{idx}", sk, sk ** j)
+            x = residual_stack(x, params, f"{n_prefix}.{idx}", sk, sk ** j,
+                               use_causal_conv=cfg.get("use_causal_conv", False))
             idx += 1
     return x, idx
 
@@ -306,7 +355,9 @@ def melgan_inference(params, cfg, c):
 
 
 def _basis_pass(params, cfg, c):
-    x, _ = _melgan_body(params, cfg, c)
+    x, idx = _melgan_body(params, cfg, c)
+    if cfg.get("lastlinear", False):                                            # basis_melgan.py:117-118
+        x = last_linear(x, params, f"melgan.{idx}")
     if cfg.get("use_final_nonlinear_activation", True):
         x = np.maximum(x, 0)                                                    # ReLU, basis_melgan.py:121
     weight = np.ascontiguousarray(x.transpose(0, 2, 1))

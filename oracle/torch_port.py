@@ -50,13 +50,36 @@ def resblock2(x, params, prefix, k, dils):  # modules.py:247-252
     return x
 
 
-def residual_stack(c, params, prefix, k, d):  # modules.py:353-382
+def upsample_layer(x, w, b, rate, padding):  # modules.py:160-177 (Stretch2d nearest on time, then Conv1d)
+    x = F.interpolate(x.unsqueeze(1), scale_factor=(1, rate), mode="nearest").squeeze(1)
+    return F.conv1d(x, w, b, padding=padding)
+
+
+def residual_stack(c, params, prefix, k, d, causal=False):  # modules.py:343-382
     h = F.leaky_relu(c, 0.2)
-    h = F.pad(h, ((k - 1) // 2 * d,) * 2, mode="reflect")
-    h = F.conv1d(h, params[f"{prefix}.stack.2.weight"], _p(params, f"{prefix}.stack.2.bias"), dilation=d)
-    h = F.leaky_relu(h, 0.2)
-    h = F.conv1d(h, params[f"{prefix}.stack.4.weight"], _p(params, f"{prefix}.stack.4.bias"))
+    if causal:  # CausalConv1d, modules.py:273-297: ReflectionPad1d((k-1)*d) both sides, conv, keep the first T
+        T = h.size(2)
+        h = F.pad(h, ((k - 1) * d,) * 2, mode="reflect")
+        h = F.conv1d(h, params[f"{prefix}.stack.1.conv.weight"], _p(params, f"{prefix}.stack.1.conv.bias"),
+                     dilation=d)[:, :, :T]
+        h = F.leaky_relu(h, 0.2)
+        h = F.conv1d(h, params[f"{prefix}.stack.3.weight"], _p(params, f"{prefix}.stack.3.bias"))
+    else:
+        h = F.pad(h, ((k - 1) // 2 * d,) * 2, mode="reflect")
+        h = F.conv1d(h, params[f"{prefix}.stack.2.weight"], _p(params, f"{prefix}.stack.2.bias"), dilation=d)
+        h = F.leaky_relu(h, 0.2)
+        h = F.conv1d(h, params[f"{prefix}.stack.4.weight"], _p(params, f"{prefix}.stack.4.bias"))
     return h + F.conv1d(c, params[f"{prefix}.skip_layer.weight"], _p(params, f"{prefix}.skip_layer.bias"))
+
+
+def last_linear(x, params, prefix):  # modules.py:116-132, eval-mode BatchNorm1d
+    def bn(x, q):
+        return F.batch_norm(x, params[f"{q}.running_mean"], params[f"{q}.running_var"], params[f"{q}.weight"],
+                            params[f"{q}.bias"], False, 0.1, 1e-5)
+    x = bn(F.leaky_relu(x, 0.2), f"{prefix}.bn_1")
+    x = F.conv1d(x, params[f"{prefix}.linear_1.weight"], _p(params, f"{prefix}.linear_1.bias"))
+    x = bn(F.leaky_relu(x, 0.2), f"{prefix}.bn_2")
+    return F.conv1d(x, params[f"{prefix}.linear_2.weight"], _p(params, f"{prefix}.linear_2.bias"))
 
 
 def overlap_and_add(signal, frame_step):  # modules.py:34-73
@@ -105,8 +128,11 @@ def _hifigan_trunk(params, cfg, x):  # hifigan.py:92-106 / multiband_hifigan.py:
     x = F.conv1d(x, params["conv_pre.weight"], _p(params, "conv_pre.bias"), padding=3)
     for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
         x = F.leaky_relu(x, LRELU_SLOPE)
-        x = F.conv_transpose1d(x, params[f"ups.{i}.weight"], _p(params, f"ups.{i}.bias"), stride=u,
-                               padding=u // 2 + u % 2, output_padding=u % 2)
+        if cfg.get("transposedconv", True) == False:   # noqa: E712  hifigan.py:31-38
+            x = upsample_layer(x, params[f"ups.{i}.conv.weight"], _p(params, f"ups.{i}.conv.bias"), u, k // 2)
+        else:
+            x = F.conv_transpose1d(x, params[f"ups.{i}.weight"], _p(params, f"ups.{i}.bias"), stride=u,
+                                   padding=u // 2 + u % 2, output_padding=u % 2)
         xs = None
         for j in range(nk):
             r = rb(x, params, f"resblocks.{i * nk + j}", rks[j], rds[j])
@@ -135,11 +161,15 @@ def _melgan_body(params, cfg, c):  # melgan.py:66-112, basis_melgan.py:70-125
     idx = 2
     for u in cfg["upsample_scales"]:
         x = F.leaky_relu(x, 0.2)
-        x = F.conv_transpose1d(x, params[f"melgan.{idx + 1}.weight"], _p(params, f"melgan.{idx + 1}.bias"),
-                               stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
+        if cfg.get("transposedconv", True) == False and "L" in cfg:   # noqa: E712  basis_melgan.py:82-88 only
+            x = upsample_layer(x, params[f"melgan.{idx + 1}.conv.weight"], _p(params, f"melgan.{idx + 1}.conv.bias"), u, u)
+        else:
+            x = F.conv_transpose1d(x, params[f"melgan.{idx + 1}.weight"], _p(params, f"melgan.{idx + 1}.bias"),
+                                   stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
         idx += 2
         for j in range(cfg["stacks"]):
-            x = residual_stack(x, params, f"melgan.{idx}", cfg["stack_kernel_size"], cfg["stack_kernel_size"] ** j)
+            x = residual_stack(x, params, f"melgan.{idx}", cfg["stack_kernel_size"], cfg["stack_kernel_size"] ** j,
+                               causal=cfg.get("use_causal_conv", False))
             idx += 1
     return x, idx
 
@@ -154,7 +184,9 @@ def melgan_forward(params, cfg, c):  # melgan.py:125-136
 
 
 def _basis_pass(params, cfg, c):
-    x, _ = _melgan_body(params, cfg, c)
+    x, idx = _melgan_body(params, cfg, c)
+    if cfg.get("lastlinear", False):  # basis_melgan.py:117-118
+        x = last_linear(x, params, f"melgan.{idx}")
     weight = torch.relu(x).contiguous().transpose(1, 2)
     est = overlap_and_add(F.linear(weight, params["basis_signal.layer.weight"]), cfg["L"] // 2)
     return est, weight

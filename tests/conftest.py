@@ -12,6 +12,10 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 MODEL_KEYS = ["hifigan-light", "hifigan-large", "multiband-hifigan-light", "multiband-hifigan-large",
               "melgan-original", "basis-melgan-light"]
+# non-default architecture switches, goldens from the reference classes with the switch turned on
+VARIANT_KEYS = ["hifigan-light-upsamplelayer", "hifigan-light-resblock2", "multiband-hifigan-light-upsamplelayer",
+                "melgan-causal", "basis-melgan-upsamplelayer", "basis-melgan-causal-lastlinear"]
+ALL_KEYS = MODEL_KEYS + VARIANT_KEYS
 
 
 def pytest_configure(config):
@@ -36,5 +40,5 @@ def load_model_golden(key):
 def folded_weights(specs, key, seed=0):
     """Regenerate the deterministic weights gen_golden.py loaded into the reference."""
     from fastvocoder_b200.synthetic import synth_state_dict
-    spec = [(n, tuple(s)) for n, s in specs[key]["spec_folded"] if not n.startswith("pqmf.")]
+    spec = [(n, tuple(s)) for n, s in specs[key]["spec_folded"] if not n.startswith("pqmf.") and not n.endswith("num_batches_tracked")]
     return synth_state_dict(spec, seed=seed)

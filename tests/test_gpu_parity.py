@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_KEYS, folded_weights, load_model_golden
+from conftest import ALL_KEYS, MODEL_KEYS, VARIANT_KEYS, folded_weights, load_model_golden
 from fastvocoder_b200 import PQMF, _lib, build_generator
 from fastvocoder_b200.synthetic import synth_mel
 from oracle import np_oracle as O
@@ -208,7 +208,7 @@ def test_encode_16bits_matches_save_wav_quantiser():
 
 # ------------------------------------------------------------------------------------------ models
 @pytest.mark.parametrize("tc", [False, True])
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_model_forward_matches_reference(specs, key, tc):
     g = load_model_golden(key)
     m = make_model(specs, key, tc)
@@ -226,7 +226,7 @@ def test_model_forward_matches_reference(specs, key, tc):
 
 
 @pytest.mark.parametrize("tc", [False, True])
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_model_inference_matches_reference(specs, key, tc):
     g = load_model_golden(key)
     m = make_model(specs, key, tc)

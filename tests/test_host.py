@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, MODEL_KEYS, REPO, folded_weights
+from conftest import ALL_KEYS, GOLDEN, MODEL_KEYS, REPO, folded_weights
 from fastvocoder_b200 import _lib, build_generator
 from fastvocoder_b200.pqmf import PQMF, design_filters
 
@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().fv_abi_version() == _lib.FV_ABI_VERSION
 
 
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_state_dict_keys_match_reference(specs, key):
     m = build_generator(specs[key]["model_name"], specs[key]["config"])
     got = {k: tuple(v.shape) for k, v in m.state_dict().items()}

@@ -9,14 +9,14 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import MODEL_KEYS, folded_weights, load_model_golden
+from conftest import ALL_KEYS, folded_weights, load_model_golden
 from oracle import np_oracle as O
 from oracle import torch_port as P
 
 TOL32 = 2e-5   # fp32 summation-order noise through ~80 conv layers (measured fp32-vs-fp64: <= 4e-6)
 
 
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_numpy_oracle_forward_matches_reference(specs, key):
     g = load_model_golden(key)
     name, cfg = specs[key]["model_name"], specs[key]["config"]
@@ -31,7 +31,7 @@ def test_numpy_oracle_forward_matches_reference(specs, key):
         assert np.abs(ys[1] - g["forward1_f32"]).max() < 5e-5
 
 
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_numpy_oracle_inference_matches_reference(specs, key):
     g = load_model_golden(key)
     name, cfg = specs[key]["model_name"], specs[key]["config"]
@@ -45,7 +45,7 @@ def test_numpy_oracle_inference_matches_reference(specs, key):
         assert np.abs(y - g["realmel_inference_f32"]).max() < TOL32
 
 
-@pytest.mark.parametrize("key", MODEL_KEYS)
+@pytest.mark.parametrize("key", ALL_KEYS)
 def test_torch_port_matches_reference(specs, key):
     g = load_model_golden(key)
     name, cfg = specs[key]["model_name"], specs[key]["config"]
