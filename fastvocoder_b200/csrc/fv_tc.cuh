@@ -75,14 +75,17 @@ __device__ __forceinline__ bool mbar_try_wait_spin(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
-__device__ int g_wait_hint = 1;   // 1: try_wait with a suspend-time hint, 0: plain try_wait polling (FV_WAIT_HINT=0)
-// Bounded wait: a broken pipeline traps (launch failure reported to the host) instead of hanging the GPU.
+__device__ int g_wait_hint = 1;   // 1: try_wait with a suspend-time hint, 0: plain try_wait polling, 2: hint + nanosleep back-off (FV_WAIT_HINT)
+// Bounded wait: a broken pipeline traps (launch failure reported to the host) instead of hanging the GPU.  The bound
+// is an iteration count, not clock64(): the polling loop of the waiting roles was a third of all executed instructions
+// of the fused-unit kernel (ncu source page), competing for issue slots with the loaders / epilogues on the same SMSP.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait_spin(bar, parity)) return;
-  const long long t0 = clock64();
-  const bool hint = g_wait_hint != 0;
-  while (!(hint ? mbar_try_wait(bar, parity) : mbar_try_wait_spin(bar, parity))) {
-    if (clock64() - t0 > 400000000LL) {
+  const int mode = g_wait_hint;
+  uint32_t spins = 0;
+  while (!(mode ? mbar_try_wait(bar, parity) : mbar_try_wait_spin(bar, parity))) {
+    if (mode == 2) __nanosleep(128);
+    if (++spins > (1u << 24)) {
       printf("fv_tc: mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x);
       __trap();
@@ -163,6 +166,32 @@ __device__ __forceinline__ void umma_f16_elect(uint32_t d_tmem, uint64_t adesc, 
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A-operand collector hints: `fill` keeps the fetched A tile in the tensor core's collector buffer, `lastuse` takes A
+// from there instead of re-reading 4 KB of shared memory (SASS: UTCHMMA ...A_KEEP / ...A_REUSE).  Only valid when
+// the two UMMAs are adjacent in the tensor pipe's queue -> single-issuer plans only (tc2_plan).
+__device__ __forceinline__ void umma_f16_elect_fill(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_elect_lastuse(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// Programmatic dependent launch: the next kernel of the layer chain may start its prologue (barriers, TMEM, weight
+// image) while this one drains; it touches activations only after pdl_wait() (= all prerequisite grids complete).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // tcgen05.commit tracks the MMAs of the EXECUTING thread: it must come from the same elected lane (elect.sync is
 // deterministic for a given member mask).
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
@@ -220,6 +249,81 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi2, u
   const float l0 = x0 - h0, l1 = x1 - h1;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(h1), "f"(h0));   // d.hi = first src, d.lo = second
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(l1), "f"(l0));
+}
+
+// Flattened fill of one A stage.  The (8-channel group kc, row r) items of the stage are dealt round-robin over the
+// 256 loader threads: item i = kc * rows + r, thread ltid takes i = ltid + 256 t.  Every thread then has `per` items =
+// 8 * per independent global loads in flight per round, and a stage whose row count is not a multiple of 128 (every
+// tile with a halo) no longer pays a whole extra DRAM round trip for a few leftover rows.  `src(kc, ptr, slope)`
+// yields the channel-group base pointer (row stride `lstride` floats between channels) and its pre-activation.
+// LeakyReLU for slopes known to lie in [0, 1] (the fused-unit kernel: always an activation): one FMUL + one FMNMX
+__device__ __forceinline__ float lrelu01(float v, float slope) { return fmaxf(v, v * slope); }
+
+// Materialise a base pointer so that `base + int_index` becomes one IMAD.WIDE (the compiler otherwise re-associates
+// the 64-bit element offsets of the whole expression: five integer instructions per global access).
+template <class T>
+__device__ __forceinline__ T* opaque_ptr(T* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+constexpr int LD_MAX = 5;
+// All offsets inside one utterance's [C, L] plane are 32-bit element indices (the planners reject planes >= 2^31
+// elements): one IMAD.WIDE per global address instead of a chain of 64-bit multiplies and adds — these kernels are
+// bound by the instruction stream of their loader / epilogue warps (ncu: 60-65 % issue-slot utilisation, of which the
+// address arithmetic was the largest part).
+template <bool ACT01 = false, class Src>
+__device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, int rows, int nkc, int ltid, int per,
+                                                int rounds, int g0, int Lb, int lstride, bool reflect, Src src) {
+  const int nitems = nkc * rows;
+  const uint32_t ls = (uint32_t)lstride;   // unsigned: keeps c * ls a 32-bit multiply feeding one IMAD.WIDE.U32
+  const int kstep = 256 / rows, rstep = 256 - kstep * rows;   // item + 256 -> (kc + kstep, r + rstep) with one carry
+  int i0 = ltid;
+  int kc0 = i0 / rows, r0 = i0 - kc0 * rows;
+  for (int rd = 0; rd < rounds; ++rd) {
+    float v[LD_MAX][8];
+    float sl[LD_MAX];
+    int ofs[LD_MAX];
+#pragma unroll
+    for (int t = 0; t < LD_MAX; ++t) {
+      const bool live = t < per && i0 < nitems;
+      const int kc = live ? kc0 : 0;
+      const float* xc;
+      src(kc, xc, sl[t]);
+      int g = g0 + r0;
+      if (reflect) {
+        if (g < 0) g = -g;
+        if (g >= Lb) g = 2 * (Lb - 1) - g;
+      }
+      const bool ok = live && g >= 0 && g < Lb;
+      const float* pg = opaque_ptr(xc + (ok ? g : 0));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(pg + (uint32_t)c * ls) : 0.f;
+      ofs[t] = live ? (kc * rows + r0) * 16 : -1;
+      if (t < per) {   // advance to item i0 + 256
+        i0 += 256; kc0 += kstep; r0 += rstep;
+        if (r0 >= rows) { r0 -= rows; ++kc0; }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < LD_MAX; ++t) {
+      if (ofs[t] < 0) continue;
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        if (ACT01) split_f16x2(lrelu01(v[t][c], sl[t]), lrelu01(v[t][c + 1], sl[t]), hp[c >> 1], lp[c >> 1]);
+        else split_f16x2(pre_act(v[t][c], sl[t]), pre_act(v[t][c + 1], sl[t]), hp[c >> 1], lp[c >> 1]);
+      }
+      *reinterpret_cast<uint4*>(A_hi + ofs[t]) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(A_lo + ofs[t]) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+  }
+}
+// rounds / items per thread per round for a stage of `nitems` items
+inline void flat_plan(int nitems, int& per, int& rounds) {
+  rounds = (nitems + 256 * LD_MAX - 1) / (256 * LD_MAX);
+  if (rounds < 1) rounds = 1;
+  per = (nitems + 256 * rounds - 1) / (256 * rounds);
+  if (per < 1) per = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,7 +460,7 @@ constexpr int TC2_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 4) * 32;  // 8
 // issuer (A rows mt_step16 / accumulator columns d_step apart).  Everything is warp-uniform; MT is unrolled so the
 // per-UMMA overhead is one or two uniform adds.  DUAL: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs per block,
 // hi*lo terms in their own accumulator columns); else three N = NT UMMAs into the same columns.
-template <bool DUAL, int MT>
+template <bool DUAL, int MT, bool REUSE = false>
 __device__ __forceinline__ void issue_kblocks(uint64_t ad, uint64_t bd, uint32_t d0, int nkb, uint32_t accum,
                                               uint64_t ks_step16, uint64_t kb16, uint64_t mt_step16, uint32_t d_step,
                                               uint64_t lo_delta16, uint64_t nt16, uint32_t idesc, uint32_t idesc2) {
@@ -368,6 +472,10 @@ __device__ __forceinline__ void issue_kblocks(uint64_t ad, uint64_t bd, uint32_t
       if (DUAL) {
         umma_f16_elect(d, am, bd, idesc2, accum);               // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
         umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);      // lo*hi -> cols [0,NT)
+      } else if (REUSE) {   // single issuer: the hi tile is fetched once for its two products
+        umma_f16_elect_fill(d, am, bd, idesc, accum);
+        umma_f16_elect_lastuse(d, am, bd + nt16, idesc, 1u);
+        umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);
       } else {
         umma_f16_elect(d, am, bd, idesc, accum);
         umma_f16_elect(d, am, bd + nt16, idesc, 1u);            // + NT*16 bytes: the lo half of the block
@@ -389,6 +497,9 @@ struct Tc2Args {
   int cluster_mode;  // experimental (FV_CLUSTER): 1 = pairs, private weight copies; 2 = each CTA multicasts its half; 3 = rank 0 multicasts all
   int n_issuers;     // UMMA issuer warps in use (1..4; at most 3 when the weight ring needs warp 11)
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
+  int a_reuse;       // three-UMMA form, one issuer: A_hi stays in the collector for its second product
+  int ld_per, ld_rounds;   // flattened loader: items per thread per round / rounds per A stage (0 = legacy pair loop)
+  int pdl;           // launched with programmatic stream serialization
   uint32_t idesc;    // M=128, N=NT
   uint32_t idesc2;   // M=128, N=2*NT (dual)
   long long* dbg;    // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
@@ -436,25 +547,26 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
       }
       if (DBG) { const long long t1 = clock64(); wa.w[1] += t1 - tdbg; tdbg = t1; }   // "tmem": TMEM read + wait::ld
-      long long o0, ostride;
+      int o0, ostride;   // 32-bit offsets inside the utterance's output plane (tc2_plan rejects planes >= 2^31 elements)
       bool ok = pos < a.Lpos;
       if (LAYOUT == OUT_BCL) {
-        o0 = (long long)nbase * a.Lpos + pos; ostride = a.Lpos;
+        o0 = nbase * a.Lpos + pos; ostride = a.Lpos;
       } else if (LAYOUT == OUT_BLC) {
-        o0 = (long long)pos * a.N + nbase; ostride = 1;
+        o0 = pos * a.N + nbase; ostride = 1;
       } else {
         const int t = pos * a.ph_stride + r - a.ph_pad;
         ok = ok && t >= 0 && t < a.ph_lout;
-        o0 = (long long)co0 * a.ph_lout + t; ostride = a.ph_lout;
+        o0 = co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
       if (!ok) continue;
+      float* py = opaque_ptr(yb + o0);
       if (LAYOUT != OUT_PHASE && nbase + 16 > a.N) {   // zero-padded tail columns (Basis 15 of 16, conv_post 1 / 4 of 16)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (nbase + i < a.N) {
             float vv = __uint_as_float(rr[i]) + (a.bias ? __ldg(a.bias + nbase + i) : 0.f);
             if (a.post_tanh) vv = tanhf(vv);
-            yb[o0 + i * ostride] = vv;
+            py[(uint32_t)i * (uint32_t)ostride] = vv;
           }
         }
         continue;
@@ -467,7 +579,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = v[i];
+      for (int i = 0; i < 16; ++i) py[(uint32_t)i * (uint32_t)ostride] = v[i];
       if (DBG) wa.w[4] += clock64() - tdbg;      // "store": bias add + issuing the 16 stores
     }
   }
@@ -486,23 +598,25 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
   const int n_it = nchunks * p.m_tiles;          // iteration = (chunk c, M tile mt), mt fastest
   // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division, far inside 1e-4
   const float inv = a.acc_mode == ACC_ADD_DIV ? 1.0f / a.acc_div : 1.0f;
-  const long long ostride = a.Lpos;
+  const int ostride = a.Lpos;   // 32-bit offsets inside the utterance plane (tc2_plan)
+  const uint32_t uos = (uint32_t)ostride;
   const int row = q * 32 + lane;
   // The residual of iteration it+1 is requested before iteration it is processed (software pipelining: two sets of
   // loads in flight per warp instead of one; these four warps are latency-bound, not bandwidth-bound).
   float nxt[16];
   {
     const bool ok0 = t0 + row < a.Lpos;
-    const long long o = (long long)(nt * p.NT) * a.Lpos + t0 + row;
+    const int o = (nt * p.NT) * a.Lpos + t0 + row;
+    const float* pr = opaque_ptr(rb + ((rb && ok0) ? o : 0));
 #pragma unroll
-    for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok0) ? __ldg(rb + o + i * ostride) : 0.f;
+    for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok0) ? __ldg(pr + (uint32_t)i * uos) : 0.f;
   }
   int c = 0, mt = 0;
   for (int it = 0; it < n_it; ++it) {
     const int nbase = nt * p.NT + c * 16;
     const int pos = t0 + mt * 128 + row;
     const bool ok = pos < a.Lpos;
-    const long long o0 = (long long)nbase * a.Lpos + pos;
+    const int o0 = nbase * a.Lpos + pos;
     float addend[16];
     long long tld = 0;
     if (DBG) tld = clock64();
@@ -513,13 +627,15 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
     if (it + 1 < n_it) {
       const int pos2 = t0 + mt2 * 128 + row;
       const bool ok2 = pos2 < a.Lpos;
-      const long long o2 = (long long)(nt * p.NT + c2 * 16) * a.Lpos + pos2;
+      const int o2 = (nt * p.NT + c2 * 16) * a.Lpos + pos2;
+      const float* pr = opaque_ptr(rb + ((rb && ok2) ? o2 : 0));
 #pragma unroll
-      for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok2) ? __ldg(rb + o2 + i * ostride) : 0.f;
+      for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok2) ? __ldg(pr + (uint32_t)i * uos) : 0.f;
     }
+    float* py = opaque_ptr(yb + (ok ? o0 : 0));
     if (a.acc_mode != ACC_STORE) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) addend[i] += ok ? yb[o0 + i * ostride] : 0.f;
+      for (int i = 0; i < 16; ++i) addend[i] += ok ? py[(uint32_t)i * uos] : 0.f;
     }
     uint32_t rr[16];
     const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
@@ -552,7 +668,7 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) yb[o0 + i * ostride] = (__uint_as_float(rr[i]) + addend[i]) * inv;
+      for (int i = 0; i < 16; ++i) py[(uint32_t)i * uos] = (__uint_as_float(rr[i]) + addend[i]) * inv;
     }
     if (DBG) wa.w[4] += clock64() - tdbg;        // "store": bias add + issuing the 16 stores
     c = c2; mt = mt2;
@@ -583,6 +699,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform -> uniform-register code
   const int nt = blockIdx.y;
   const int M = p.m_tiles * 128;
+  if (p.pdl) pdl_launch_dependents();   // the next layer's CTAs may take over SMs as soon as ours retire
   const uint8_t* wsrc = p.wimg + (size_t)nt * p.kblocks * kblock_bytes;
   // Weight-ring multicast: the CTAs of a cluster (launched as pairs for ring-mode layers) walk the same number of
   // ring iterations; each fetches 1/cs of every stage and multicasts it to all of them.
@@ -620,6 +737,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     int u = 0;                                  // A-stage unit counter: (tile, channel chunk)
     WaitAcc<DBG> wa;
     wa.begin();
+    if (p.pdl) pdl_wait();                      // activations of the previous layer are complete and visible
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
@@ -630,6 +748,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         if (u >= p.a_stages) wa.wait(0, BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
         uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
         uint8_t* A_lo = A_hi + a_bytes;
+        if (p.ld_per > 0) {
+          fill_stage_flat(A_hi, A_lo, rows, nkc, warp * 32 + lane, p.ld_per, p.ld_rounds, t0 - a.pad_left, Lb,
+                          a.Lin, a.pad_mode == PAD_REFLECT, [&](int kc, const float*& xc, float& slope) {
+                            const int cg = ch * p.ck + kc * 8;
+                            const bool second = a.cin_split > 0 && cg >= a.cin_split;
+                            xc = second ? a.x2 + (long long)b * a.x2_bs + (long long)(cg - a.cin_split) * a.Lin
+                                        : xb + (long long)cg * a.Lin;
+                            slope = second ? a.pre_slope2 : a.pre_slope;
+                          });
+        } else
         for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
           const int kc = pr / nrb, rbk = pr - kc * nrb;
           const int cg = ch * p.ck + kc * 8;                     // first of 8 global input channels of this group
@@ -649,8 +777,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
               if (g >= Lb) g = 2 * (Lb - 1) - g;
             }
             const bool ok = r < rows && g >= 0 && g < Lb;
+            const float* pg = opaque_ptr(xc + (ok ? g : 0));
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * a.Lin + g) : 0.f;
+            for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(pg + (uint32_t)c * (uint32_t)a.Lin) : 0.f;
           }
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -753,7 +882,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         const uint32_t d_step = acc_mt_cols * (uint32_t)p.n_issuers;
         const uint32_t idesc = p.idesc, idesc2 = p.idesc2;
         const int K = a.K, dil = a.dil, m_tiles = p.m_tiles, n_iss = p.n_issuers;
-        const bool dual = p.dual != 0, resident = p.w_resident != 0;
+        const bool dual = p.dual != 0, resident = p.w_resident != 0, reuse = p.a_reuse != 0;
         const uint32_t kb16 = (uint32_t)kblock_bytes >> 4;                  // one weight k-block, in 16-B units
         const uint64_t nt16 = (uint64_t)p.NT;
         const uint64_t ks_step16 = 2ull * (uint64_t)rows;                   // next 16-channel k-step of the A stage
@@ -784,6 +913,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                   case 3: FV_ISSUE(true, 3); break;
                   default: FV_ISSUE(true, 4); break;
                 }
+              } else if (reuse) {
+#define FV_ISSUE_R(M) issue_kblocks<false, M, true>(ad, bd, acc, nkb, accum, ks_step16, (uint64_t)kb16, (uint64_t)mt_step16, d_step, \
+                                                    (uint64_t)a_lo_delta, nt16, idesc, idesc2)
+                switch (my_mts) {
+                  case 1: FV_ISSUE_R(1); break;
+                  case 2: FV_ISSUE_R(2); break;
+                  case 3: FV_ISSUE_R(3); break;
+                  default: FV_ISSUE_R(4); break;
+                }
+#undef FV_ISSUE_R
               } else {
                 switch (my_mts) {
                   case 1: FV_ISSUE(false, 1); break;
@@ -840,6 +979,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
     int it = 0;
     WaitAcc<DBG> wa;
     wa.begin();
+    if (p.pdl) pdl_wait();   // residual / running-sum reads and all stores come after the previous layer
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it % p.acc_stages;
       wa.wait(0, BAR(4 + as), (uint32_t)((it / p.acc_stages) & 1), 700 + as);
@@ -882,6 +1022,11 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const int need_mt = (a.Lpos + 127) / 128;
   static const int force_dual = getenv("FV_TC2_DUAL") ? atoi(getenv("FV_TC2_DUAL")) : -1;   // tuning knob: 0 / 1
   if ((a.res != nullptr || a.acc_mode != ACC_STORE) && (a.out_layout != OUT_BCL || a.post_tanh)) return false;
+  {  // the kernels index inside one utterance's input / output plane with 32-bit element offsets
+    const long long lim = 0x7fffffffLL - 65536;
+    const long long out_plane = a.out_layout == OUT_PHASE ? (long long)a.ph_cout * a.ph_lout : (long long)L.n_pad * a.Lpos;
+    if ((long long)a.Cin * a.Lin >= lim || out_plane >= lim) return false;
+  }
   struct Cand { int mt, a_st, res, w_st, ck, kbps, dual; double score; };
   Cand best{0, 0, 0, 0, 0, 0, 0, -1.0};
   // Cycle model per CTA tile, calibrated on B200 (profiles/r01_notes.md, scripts/probes/umma_issue_probe.cu and the
@@ -975,6 +1120,15 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
     p.n_issuers = ni < 1 ? 1 : ni;
   }
   p.dual = dualf == 2 ? 1 : 0;
+  // A-collector reuse (three-UMMA form): needs the fill / lastuse pair adjacent in the tensor pipe -> one issuer, which
+  // is enough when every UMMA runs >= 64 clk (NT >= 128) against ~20 clk of issue cost
+  static const int reuse_env = getenv("FV_A_REUSE") ? atoi(getenv("FV_A_REUSE")) : 0;
+  p.a_reuse = (reuse_env && !p.dual && NT >= 128 && best.mt <= 4) ? 1 : 0;
+  if (p.a_reuse) p.n_issuers = 1;
+  static const int flat_env = getenv("FV_LOADER_FLAT") ? atoi(getenv("FV_LOADER_FLAT")) : 1;
+  p.ld_per = p.ld_rounds = 0;
+  // conv_tc2: measured mixed (C=64/128 k=11 -7 %, Cin=512 pair layers +9 %) -> opt-in with FV_LOADER_FLAT=2
+  if (flat_env >= 2) flat_plan((best.ck / 8) * (best.mt * 128 + halo), p.ld_per, p.ld_rounds);
   p.acc_cols = best.mt * NT * dualf;
   p.acc_stages = (2 * p.acc_cols <= 512) ? 2 : 1;
   int cols = 32;
@@ -996,6 +1150,14 @@ inline void tc_apply_env_once() {
     int v = atoi(e);
     cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(int));
   }
+}
+
+// FV_PDL=1: launch the tensor-core kernels of the layer chain with programmatic stream serialization (the next
+// layer's prologue overlaps this layer's tail).  Correct (GPU tests pass with it) but measured neutral-to-slower on the
+// B=32 step (19.7 -> 20.1 ms, profiles/r01_notes.md "ab2"), so it stays opt-in.
+inline bool tc_pdl_enabled() {
+  static const bool on = getenv("FV_PDL") != nullptr && atoi(getenv("FV_PDL")) != 0;
+  return on;
 }
 
 // FV_STALL_DEBUG=1: launch the instrumented instantiation, synchronise and print where each role waited (stderr).
@@ -1079,13 +1241,19 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   cfg.blockDim = dim3(TC2_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  p.pdl = (tc_pdl_enabled() && cs == 1 && !tc_stall_debug()) ? 1 : 0;
+  if (p.pdl) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t le;
   if (tc_stall_debug()) {
     StallReport rep;
@@ -1145,6 +1313,8 @@ struct Tc3Args {
   int ksteps, kblocks;
   int tiles_per_batch, total_tiles;
   uint32_t idesc, idesc2;
+  int ld_per, ld_rounds;   // flattened loader (fill_stage_flat); 0 = legacy pair loop
+  int pdl;                 // launched with programmatic stream serialization
   long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
@@ -1187,6 +1357,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
+  if (p.pdl) pdl_launch_dependents();
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -1220,6 +1391,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     int it = 0;
     WaitAcc<DBG> wa;
     wa.begin();
+    if (p.pdl) pdl_wait();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int s = it % p.a1_stages;
       if (it >= p.a1_stages) wa.wait(0, BAR(2 + s), (uint32_t)((it / p.a1_stages - 1) & 1), 800 + s);
@@ -1229,6 +1401,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       const int Lb = p.lens ? __ldg(p.lens + b) : p.L;
       uint8_t* A_hi = A1 + (size_t)s * 2 * a1_bytes;
       uint8_t* A_lo = A_hi + a1_bytes;
+      if (p.ld_per > 0) {
+        const float slope1 = p.slope;
+        fill_stage_flat<true>(A_hi, A_lo, rows, nkc, warp * 32 + lane, p.ld_per, p.ld_rounds, t0 - p2 - p1, Lb, p.L,
+                        false, [&](int kc, const float*& xc, float& slope) {
+                          xc = xb + (long long)(kc * 8) * p.L;
+                          slope = slope1;
+                        });
+      } else
       for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
         const int kc = pr / nrb, rbk = pr - kc * nrb;
         const float* __restrict__ xc = xb + (long long)(kc * 8) * p.L;
@@ -1240,8 +1420,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           rrow[t] = r;
           const int g = t0 - p2 - p1 + r;
           const bool ok = r < rows && g >= 0 && g < Lb;
+          const float* pg = opaque_ptr(xc + (ok ? g : 0));
 #pragma unroll
-          for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(xc + (long long)c * p.L + g) : 0.f;
+          for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(pg + (uint32_t)c * (uint32_t)p.L) : 0.f;
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -1249,7 +1430,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           uint32_t hp[4], lp[4];
 #pragma unroll
           for (int c = 0; c < 8; c += 2)
-            split_f16x2(pre_act(v[t][c], p.slope), pre_act(v[t][c + 1], p.slope), hp[c >> 1], lp[c >> 1]);
+            split_f16x2(lrelu01(v[t][c], p.slope), lrelu01(v[t][c + 1], p.slope), hp[c >> 1], lp[c >> 1]);
           const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
           *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
@@ -1381,8 +1562,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
         for (int c = 0; c < nchunks; ++c) {
           float b1v[16];
+          if (p.bias1) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias1 + c * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) b1v[i] = p.bias1 ? __ldg(p.bias1 + c * 16 + i) : 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = __ldg(bp + i);
+              b1v[4 * i] = bv.x; b1v[4 * i + 1] = bv.y; b1v[4 * i + 2] = bv.z; b1v[4 * i + 3] = bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) b1v[i] = 0.f;
+          }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
             const int r = mt * 128 + q * 32 + lane;
             const int gpos = t0 - p2 + r;
@@ -1392,13 +1582,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             tmem_ld16(tcol, rr);
             tmem_ld16(tcol + (uint32_t)NT, r2);
             uint32_t hp[8], lp[8];
+            const uint32_t keep = inside ? 0xffffffffu : 0u;   // rows outside the sequence are conv2's zero padding
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
-              float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]) + b1v[i];
-              float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]) + b1v[i + 1];
-              v0 = inside ? pre_act(v0, p.slope) : 0.f;
-              v1 = inside ? pre_act(v1, p.slope) : 0.f;
-              split_f16x2(v0, v1, hp[i >> 1], lp[i >> 1]);
+              const float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]) + b1v[i];
+              const float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]) + b1v[i + 1];
+              split_f16x2(lrelu01(v0, p.slope), lrelu01(v1, p.slope), hp[i >> 1], lp[i >> 1]);
+              hp[i >> 1] &= keep;
+              lp[i >> 1] &= keep;
             }
             const uint32_t off0 = ((uint32_t)(2 * c) * p.h_rows_alloc + r) * 16;
             const uint32_t off1 = ((uint32_t)(2 * c + 1) * p.h_rows_alloc + r) * 16;
@@ -1425,6 +1616,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     int it = 0;
     WaitAcc<DBG> wa;
     wa.begin();
+    if (p.pdl) pdl_wait();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
@@ -1433,24 +1625,36 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         const float* __restrict__ xb = p.x + (long long)b * C * p.L;
         float* __restrict__ yb = p.y + (long long)b * C * p.L;
         const float inv = 1.0f / p.acc_div;
+        const uint32_t uL = (uint32_t)p.L;
         const uint32_t acc2 = acc2_base + (uint32_t)(bs * p.acc_cols);
         bool waited = false;
         for (int c = 0; c < nchunks; ++c) {
           float bias[16];
+          if (p.bias2) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + c * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) bias[i] = p.bias2 ? __ldg(p.bias2 + c * 16 + i) : 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = __ldg(bp + i);
+              bias[4 * i] = bv.x; bias[4 * i + 1] = bv.y; bias[4 * i + 2] = bv.z; bias[4 * i + 3] = bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bias[i] = 0.f;
+          }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
             const int r = mt * 128 + q * 32 + lane;
             const int t = t0 + r;
             const bool ok = r < p.m_out && t < p.L;
-            const long long o0 = (long long)(c * 16) * p.L + t;
+            const int o0 = (c * 16) * p.L + t;   // 32-bit offset inside the utterance plane (tc3_plan: C*L < 2^31)
             // the residual does not depend on the accumulators: issue its loads before waiting for the UMMAs
             float xv[16];
+            const float* px = opaque_ptr(xb + (ok ? o0 : 0));
+            float* py = opaque_ptr(yb + (ok ? o0 : 0));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(xb + o0 + (long long)i * p.L) : 0.f;
+            for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(px + (uint32_t)i * uL) : 0.f;
             if (p.acc_mode != ACC_STORE) {   // running MRF sum: fold it into the prefetched addend (x + xs)
 #pragma unroll
-              for (int i = 0; i < 16; ++i) xv[i] += ok ? yb[o0 + (long long)i * p.L] : 0.f;
+              for (int i = 0; i < 16; ++i) xv[i] += ok ? py[(uint32_t)i * uL] : 0.f;
             }
             if (!waited) {
               wa.wait(0, BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
@@ -1471,7 +1675,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               for (int i = 0; i < 16; ++i) v[i] *= inv;
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) yb[o0 + (long long)i * p.L] = v[i];
+            for (int i = 0; i < 16; ++i) py[(uint32_t)i * uL] = v[i];
           }
         }
         tc_fence_before();
@@ -1494,6 +1698,7 @@ inline size_t tc3_smem_bytes(const Tc3Args& p) {
 // conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64)
 inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   if (C % 16 || C > 64 || K % 2 == 0) return false;
+  if ((long long)C * L >= 0x7fffffffLL - 65536) return false;   // 32-bit offsets inside the utterance plane
   const int ksteps = C / 16, kblocks = K * ksteps;
   const long long BUDGET = 225 * 1024;
   int best_m = 0, best_a1 = 0, best_acc1 = 0;
@@ -1542,6 +1747,13 @@ retry:
   p.total_tiles = p.tiles_per_batch * B;
   p.idesc = make_idesc_f16(128, C);
   p.idesc2 = make_idesc_f16(128, 2 * C);
+  static const int flat_env = getenv("FV_LOADER_FLAT") ? atoi(getenv("FV_LOADER_FLAT")) : 1;
+  p.ld_per = p.ld_rounds = 0;
+  // measured (profiles/r01_notes.md, ab2 / ab3): flat wins where the unit is loader-bound and the pair loop needs a second
+  // round (k = 3 with more than 8 pairs: C=32 -6 %); it loses where the pair loop is one round (C=16 k=3 +15 %) and on the
+  // issue-bound k = 7 / 11 units (C=32 k=11 +18 %)
+  if ((flat_env >= 2 || (flat_env && K <= 3)) && (C / 8) * ((p.x_rows + 127) / 128) > TC2_LOADER_WARPS)
+    flat_plan((C / 8) * p.x_rows, p.ld_per, p.ld_rounds);
   return true;
 }
 
@@ -1552,6 +1764,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
   if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
   tc_apply_env_once();
   Tc3Args p{};
+  if (!(slope >= 0.f && slope <= 1.f)) return 1;   // lrelu01
   if (!tc3_plan(B, C, L, K, dil, p)) return 1;
   p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2; p.lens = lens;
   p.w1img = l1.image; p.w2img = l2.image;
@@ -1573,6 +1786,19 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     attr_set[dev] = true;
   }
   int gx = std::min(num_sms[dev], p.total_tiles);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(gx, 1, 1);
+  cfg.blockDim = dim3(TC3_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc3_smem_bytes(p);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  p.pdl = (tc_pdl_enabled() && !tc_stall_debug()) ? 1 : 0;
+  if (p.pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
   if (tc_stall_debug()) {
     StallReport rep;
     if (!rep.begin(gx)) return -1;
@@ -1591,7 +1817,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
              K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.n_issuers, p.total_tiles, gx);
     rep.finish(st, title, roles, slots);
   } else {
-    conv_tc3_fused_kernel<false><<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
+    if (cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false>, p) != cudaSuccess) return -1;
   }
   g_launches++;
   g_tc_launches++;
