@@ -335,10 +335,10 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         weights = {k: v.numpy() for k, v in synthetic_weights(model).items()}
-        utts = 2
-        v, dt = cpu_port_throughput(name, cfg, weights, T, utts, repeats=2)
+        utts = min(B, 16)                            # bounded sample: ~10-20 s of CPU work in total
+        v, dt = cpu_port_throughput(name, cfg, weights, T, utts, repeats=3)
         cpu_baseline = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{utts} utterances x {T} frames, best of 2 after warm-up ({dt:.2f} s each), "
+                        "sample": f"{utts} of the {B} utterances x {T} frames, best of 3 after warm-up ({dt:.2f} s each), "
                                   "ATen port of the reference CPU path (oracle/torch_port.py)"}
 
     if rank == 0:
