@@ -331,6 +331,39 @@ def main():
                 json.dump({"workload": label, "B": B, "T": T, "layers": prof, "by_kernel": roofline["by_kernel"]}, f,
                           indent=1)
 
+    # ---- standalone HBM-bound pieces of the path: GB/s of algorithmic bytes vs the measured copy peak ----
+    hbm_kernels = None
+    if rank == 0:
+        from fastvocoder_b200 import PQMF
+        from fastvocoder_b200.synthesizer import encode_16bits
+        peaks = measured_peaks()
+        pq = PQMF().to(dev)
+        Bq, Lq = 64, 60 * T                           # configs[3]: sub-bands [64, 4, 60 T] -> wave [64, 1, 240 T]
+        xs = torch.rand(Bq, 4, Lq, device=dev) - 0.5
+        xw = torch.rand(Bq, 1, 4 * Lq, device=dev) - 0.5
+        wav = torch.rand(Bq * 4 * Lq, device=dev) - 0.5
+
+        def timed(fn, nbytes, reps=5):
+            fn()
+            best = float("inf")
+            for _ in range(reps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            gbs = nbytes / (best * 1e-3) / 1e9
+            return {"ms": best, "GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "algorithmic_bytes": nbytes}
+        with torch.no_grad():
+            hbm_kernels = {
+                "pqmf_synthesis": timed(lambda: pq.synthesis(xs), 2 * xs.numel() * 4),        # 960 B in + 960 B out / frame
+                "pqmf_analysis": timed(lambda: pq.analysis(xw), 2 * xw.numel() * 4),
+                "encode_16bits": timed(lambda: encode_16bits(wav), wav.numel() * (4 + 4 + 2)),  # peak pass + scale pass + int16 out
+                "peak": {"hbm_gbs": peaks["hbm_gbs"], "source": peaks["source"]},
+                "shape": f"B={Bq}, sub-bands 4 x {Lq}, L2 flushed before each run, best of 5",
+            }
+        del xs, xw, wav
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -340,6 +373,12 @@ def main():
         cpu_baseline = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                         "sample": f"{utts} of the {B} utterances x {T} frames, best of 3 after warm-up ({dt:.2f} s each), "
                                   "ATen port of the reference CPU path (oracle/torch_port.py)"}
+        nthreads = torch.get_num_threads()           # bin/test.py times the reference single-threaded, one utterance
+        torch.set_num_threads(1)
+        v1, dt1 = cpu_port_throughput(name, cfg, weights, T, 1, repeats=1)
+        torch.set_num_threads(nthreads)
+        cpu_baseline["value_1thread"] = v1
+        cpu_baseline["sample_1thread"] = f"1 utterance x {T} frames, 1 thread ({dt1:.2f} s)"
 
     if rank == 0:
         flops_step = model.forward_flops(B, T)
@@ -357,7 +396,7 @@ def main():
             "gpu_launches": int(launches), "tc_launches": int(tc_launches),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": 1e3 * t_e2e / args.steps},
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "hbm_kernels": hbm_kernels,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

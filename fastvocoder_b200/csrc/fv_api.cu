@@ -424,12 +424,9 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     if ((rc = call(m.post, lc))) return rc;
     if (c.kind == FV_MB_HIFIGAN && out2) {
       if (!h->pqmf_syn) return fail(FV_ESTATE, "PQMF synthesis filter not bound");
-      const int S = c.pqmf_subbands;
-      dim3 grid(grid_for(L * S), B);
-      pqmf_synthesis_kernel<<<grid, 256, S * (c.pqmf_taps + 1) * sizeof(float), st>>>(
-          out, h->pqmf_syn, out2, S, c.pqmf_taps, (int)L, lens_at((int)m.stages.size() - 1, 0));
+      FV_CUDA(launch_pqmf_synthesis(out, h->pqmf_syn, out2, B, c.pqmf_subbands, c.pqmf_taps, (int)L,
+                                    lens_at((int)m.stages.size() - 1, 0), st));
       g_launches++;
-      FV_CUDA(cudaGetLastError());
     }
   } else if (c.kind == FV_MELGAN) {  // LastLayer (modules.py:85-89) + Tanh (melgan.py:109-110)
     LayerCall lc;
@@ -780,11 +777,8 @@ int fv_pqmf_synthesis(const float* x, const float* synthesis_filter, int B, int 
                       float* y, void* stream) {
   if (!x || !synthesis_filter || !y || B <= 0 || subbands <= 0 || taps <= 0 || taps % 2 || Lband <= 0)
     return fail(FV_EINVAL, "fv_pqmf_synthesis: bad argument");
-  dim3 grid(grid_for((long long)Lband * subbands), B);
-  pqmf_synthesis_kernel<<<grid, 256, subbands * (taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
-      x, synthesis_filter, y, subbands, taps, Lband);
+  FV_CUDA(launch_pqmf_synthesis(x, synthesis_filter, y, B, subbands, taps, Lband, nullptr, (cudaStream_t)stream));
   g_launches++;
-  FV_CUDA(cudaGetLastError());
   return FV_OK;
 }
 
@@ -793,11 +787,8 @@ int fv_pqmf_analysis(const float* x, const float* analysis_filter, int B, int su
   if (!x || !analysis_filter || !y || B <= 0 || subbands <= 0 || taps <= 0 || taps % 2 || L < subbands)
     return fail(FV_EINVAL, "fv_pqmf_analysis: bad argument");
   const long long Lb = (L - subbands) / subbands + 1;  // conv1d(stride=S, kernel=S) output length
-  dim3 grid(grid_for(Lb), B);
-  pqmf_analysis_kernel<<<grid, 256, subbands * (taps + 1) * sizeof(float), (cudaStream_t)stream>>>(
-      x, analysis_filter, y, subbands, taps, (long long)L, Lb);
+  FV_CUDA(launch_pqmf_analysis(x, analysis_filter, y, B, subbands, taps, (long long)L, Lb, (cudaStream_t)stream));
   g_launches++;
-  FV_CUDA(cudaGetLastError());
   return FV_OK;
 }
 

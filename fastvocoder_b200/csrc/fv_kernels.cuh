@@ -445,6 +445,100 @@ __global__ void pqmf_synthesis_kernel(const float* __restrict__ x, const float* 
     y[(long long)b * L + t] = acc;
   }
 }
+// Polyphase form of the same sum for the shipped filterbank shape (S sub-bands, NT = taps + 1 coefficients): output
+// t = S*q + r reads x[k, q + m] * h[k, S*m - r + P] for the m with 0 <= S*m - r + P <= taps.  One thread owns one q:
+// it reads the window x[k, q + MLO .. q + MHI] of each band once (registers) and produces the S outputs of that
+// position group (one 16-byte store for S = 4) — no per-tap index division, 4 B in + 4 B out per output sample.
+// Per output the products are added in the same order as above (k ascending, then j ascending), so both kernels
+// return identical bits; out-of-range window samples contribute an exact 0 * h.
+template <int S, int NT, int QT>
+__global__ void __launch_bounds__(256) pqmf_synthesis_poly_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                                  float* __restrict__ y, int Lb,
+                                                                  const int* __restrict__ lens) {
+  constexpr int P = (NT - 1) / 2;
+  constexpr int MLO = -(P / S);
+  constexpr int MHI = (NT - 1 + S - 1 - P) / S;
+  constexpr int W = MHI - MLO + 1;
+  __shared__ float sh[S * NT];
+  // (S*x) * h == x * (S*h) exactly (S is a power of two here), so the up-sampling gain is folded into the coefficients
+  for (int i = threadIdx.x; i < S * NT; i += blockDim.x) sh[i] = (float)S * h[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  // QT position groups per thread, blockDim apart (coalesced loads / 16-byte stores): every filter coefficient read
+  // from shared memory feeds QT FMAs.  The kernel is FP32-bound, not HBM-bound: 63 FMAs per 8 bytes of traffic.
+  const int q0 = blockIdx.x * (blockDim.x * QT) + threadIdx.x;
+  const int Lv = lens ? __ldg(lens + b) : Lb;
+  // every window of this thread inside [0, Lv): no per-load bounds predicates (they were half of the instruction stream)
+  const bool interior = q0 + MLO >= 0 && q0 + (QT - 1) * (int)blockDim.x + MHI < Lv;
+  float acc[QT][S];
+#pragma unroll
+  for (int u = 0; u < QT; ++u)
+#pragma unroll
+    for (int r = 0; r < S; ++r) acc[u][r] = 0.f;
+#pragma unroll 1   // one band's windows in registers at a time (unrolled: 240 registers, one CTA per SM)
+  for (int k = 0; k < S; ++k) {
+    const float* xk = x + ((long long)b * S + k) * Lb;
+    float xw[QT][W];
+    if (interior) {
+#pragma unroll
+      for (int u = 0; u < QT; ++u) {
+        const float* xq = xk + (q0 + u * (int)blockDim.x + MLO);
+#pragma unroll
+        for (int w = 0; w < W; ++w) xw[u][w] = __ldg(xq + w);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < QT; ++u) {
+        const int q = q0 + u * (int)blockDim.x;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const int n = q + MLO + w;
+          xw[u][w] = (n >= 0 && n < Lv) ? __ldg(xk + n) : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const int j = S * (MLO + w) - r + P;   // compile-time after unrolling
+        if (j >= 0 && j < NT) {
+          const float c = sh[k * NT + j];
+#pragma unroll
+          for (int u = 0; u < QT; ++u) acc[u][r] = fmaf(xw[u][w], c, acc[u][r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < QT; ++u) {
+    const int q = q0 + u * (int)blockDim.x;
+    if (q >= Lb) continue;
+    float* yo = y + ((long long)b * Lb + q) * S;
+    if (S == 4) {
+      *reinterpret_cast<float4*>(yo) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < S; ++r) yo[r] = acc[u][r];
+    }
+  }
+}
+// host dispatch: the polyphase kernel for the reference's PQMF(subbands=4, taps=62), the generic kernel otherwise
+inline cudaError_t launch_pqmf_synthesis(const float* x, const float* h, float* y, int B, int S, int taps, int Lb,
+                                         const int* lens, cudaStream_t st) {
+  if (S == 4 && taps == 62 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    constexpr int QT = 4;
+    dim3 grid((Lb + 256 * QT - 1) / (256 * QT), B);
+    pqmf_synthesis_poly_kernel<4, 63, QT><<<grid, 256, 0, st>>>(x, h, y, Lb, lens);
+  } else {
+    long long n = (long long)Lb * S;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    dim3 grid((unsigned)g, B);
+    pqmf_synthesis_kernel<<<grid, 256, S * (taps + 1) * sizeof(float), st>>>(x, h, y, S, taps, Lb, lens);
+  }
+  return cudaGetLastError();
+}
 // analysis: a[k,n] = sum_j xpad[S*n + j] * h[k,j], xpad = zero pad P each side; n < L/S (conv1d stride S floor)
 __global__ void pqmf_analysis_kernel(const float* __restrict__ x, const float* __restrict__ h, float* __restrict__ y,
                                      int S, int taps, long long L, long long Lb) {
@@ -466,6 +560,79 @@ __global__ void pqmf_analysis_kernel(const float* __restrict__ x, const float* _
       y[((long long)b * S + k) * Lb + n] = acc;
     }
   }
+}
+
+// Same sum for the shipped shape: tap-major loop, every x sample read once and used by the S bands, every coefficient
+// vector (one 16-byte shared read) used by QT outputs (the generic kernel re-reads x per band through 64-bit index
+// arithmetic).  Same addition order per output (j ascending) -> identical bits.
+template <int S, int NT, int QT>
+__global__ void __launch_bounds__(256) pqmf_analysis_win_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                                float* __restrict__ y, int L, int Lb) {
+  constexpr int P = (NT - 1) / 2;
+  __shared__ float sh[NT * S];   // transposed [j][k]: the S coefficients of tap j are one 16-byte read
+  for (int i = threadIdx.x; i < S * NT; i += blockDim.x) sh[(i % NT) * S + i / NT] = h[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int n0 = blockIdx.x * (blockDim.x * QT) + threadIdx.x;   // QT outputs per thread, blockDim apart
+  const float* xb = x + (long long)b * L;
+  float acc[QT][S];
+#pragma unroll
+  for (int u = 0; u < QT; ++u)
+#pragma unroll
+    for (int k = 0; k < S; ++k) acc[u][k] = 0.f;
+  const bool interior = n0 * S - P >= 0 && (n0 + (QT - 1) * (int)blockDim.x) * S + (NT - 1) - P < L;
+  if (interior) {
+    const float* xq[QT];
+#pragma unroll
+    for (int u = 0; u < QT; ++u) xq[u] = xb + ((n0 + u * (int)blockDim.x) * S - P);
+#pragma unroll 9
+    for (int j = 0; j < NT; ++j) {
+      float c[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) c[k] = sh[j * S + k];
+#pragma unroll
+      for (int u = 0; u < QT; ++u) {
+        const float xv = __ldg(xq[u] + j);
+#pragma unroll
+        for (int k = 0; k < S; ++k) acc[u][k] = fmaf(xv, c[k], acc[u][k]);
+      }
+    }
+  } else {
+#pragma unroll 9
+    for (int j = 0; j < NT; ++j) {
+      float c[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) c[k] = sh[j * S + k];
+#pragma unroll
+      for (int u = 0; u < QT; ++u) {
+        const int g = (n0 + u * (int)blockDim.x) * S + j - P;
+        const float xv = (g >= 0 && g < L) ? __ldg(xb + g) : 0.f;
+#pragma unroll
+        for (int k = 0; k < S; ++k) acc[u][k] = fmaf(xv, c[k], acc[u][k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < QT; ++u) {
+    const int n = n0 + u * (int)blockDim.x;
+    if (n >= Lb) continue;
+#pragma unroll
+    for (int k = 0; k < S; ++k) y[((long long)b * S + k) * Lb + n] = acc[u][k];
+  }
+}
+inline cudaError_t launch_pqmf_analysis(const float* x, const float* h, float* y, int B, int S, int taps, long long L,
+                                        long long Lb, cudaStream_t st) {
+  if (S == 4 && taps == 62 && L < 0x7fffffffLL) {
+    constexpr int QT = 4;
+    dim3 grid((unsigned)((Lb + 256 * QT - 1) / (256 * QT)), B);
+    pqmf_analysis_win_kernel<4, 63, QT><<<grid, 256, 0, st>>>(x, h, y, (int)L, (int)Lb);
+  } else {
+    long long g = (Lb + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    dim3 grid((unsigned)g, B);
+    pqmf_analysis_kernel<<<grid, 256, S * (taps + 1) * sizeof(float), st>>>(x, h, y, S, taps, L, Lb);
+  }
+  return cudaGetLastError();
 }
 
 // overlap_and_add for frame_length == 2*step: out[n*step + j] = f[n][j] + f[n-1][step + j]  (modules.py:34-73)

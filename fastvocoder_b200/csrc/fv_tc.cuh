@@ -1315,6 +1315,11 @@ struct Tc3Args {
   uint32_t idesc, idesc2;
   int ld_per, ld_rounds;   // flattened loader (fill_stage_flat); 0 = legacy pair loop
   int pdl;                 // launched with programmatic stream serialization
+  // Streamed weights (the two images do not fit next to the tiles: C = 64, k = 7 / 11): warp 11 feeds a ring of
+  // `w_stages` slots, one slot = one tap (ksteps k-blocks = stage_bytes), in the order the issuers consume them
+  // (conv1 of tile 0, then per tile conv2(i), conv1(i+1)).  Resident mode: w_resident = 1.
+  int w_resident, w_stages, stage_bytes;
+  int acc2_stages;         // accumulator sets of conv2 (2 unless TMEM is needed for larger tiles)
   long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
@@ -1346,13 +1351,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   const uint32_t w_bytes = (uint32_t)p.kblocks * kblock_bytes;
   uint8_t* A1 = smem;                                            // [a1_stages][hi|lo]
   uint8_t* A2 = A1 + (size_t)p.a1_stages * 2 * a1_bytes;        // [hi|lo]
-  uint8_t* W1 = A2 + 2 * (size_t)a2_bytes;
+  uint8_t* W1 = A2 + 2 * (size_t)a2_bytes;                      // resident: [W1 | W2]; ring: w_stages slots
   uint8_t* W2 = W1 + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(W2 + w_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W1 + (p.w_resident ? 2 * (size_t)w_bytes : (size_t)p.w_stages * p.stage_bytes));
   // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  [10,12) acc2_full  [12,14) acc2_empty  14 w_full
+  // [15,19) ring slot full  [19,23) ring slot empty
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -1373,6 +1379,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       mbar_init(BAR(12 + s), 4);
     }
     mbar_init(BAR(14), 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(BAR(15 + s), 1);              // ring slot full: expect_tx by the producer
+      mbar_init(BAR(19 + s), p.n_issuers);    // ring slot empty: one tcgen05.commit per issuer
+    }
     fence_mbar_init();
   }
   if (warp == TC2_LOADER_WARPS) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
@@ -1380,7 +1390,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);   // two acc2 sets follow
+  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);   // the acc2 set(s) follow
+  // single-buffered A1: conv2(i) is issued before conv1(i+1) so that it never waits behind the load of the next tile
+  const bool conv2_first = p.a1_stages == 1;
 
   if (warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
@@ -1458,18 +1470,50 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     const int wid = warp - TC2_LOADER_WARPS;
     const bool L0 = (lane == 0);
     {
-      if (wid == TC2_ISSUE_WARPS - 1 && L0) {
-        mbar_expect_tx(BAR(14), 2 * w_bytes);
-        for (uint32_t off = 0; off < w_bytes; off += 32768) {
-          const uint32_t n = min(32768u, w_bytes - off);
-          bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(14));
-          bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
+      if (wid == TC2_ISSUE_WARPS - 1 && p.w_resident) {
+        if (L0) {
+          mbar_expect_tx(BAR(14), 2 * w_bytes);
+          for (uint32_t off = 0; off < w_bytes; off += 32768) {
+            const uint32_t n = min(32768u, w_bytes - off);
+            bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(14));
+            bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
+          }
         }
+      } else if (wid == TC2_ISSUE_WARPS - 1) {
+        // ring producer (n_issuers <= 3 in ring mode): one slot per tap, in the issuers' consumption order
+        WaitAcc<DBG> wa;
+        wa.begin();
+        int n_my = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) ++n_my;
+        int g = 0;
+        auto stream_conv = [&](const uint8_t* img) {
+          for (int j = 0; j < p.K; ++j, ++g) {
+            const int slot = g % p.w_stages;
+            if (g >= p.w_stages) wa.wait(0, BAR(19 + slot), (uint32_t)((g / p.w_stages - 1) & 1), 890 + slot);
+            if (L0) {
+              mbar_expect_tx(BAR(15 + slot), (uint32_t)p.stage_bytes);
+              bulk_g2s(smem_u32(W1 + (size_t)slot * p.stage_bytes), img + (size_t)j * p.stage_bytes, (uint32_t)p.stage_bytes,
+                       BAR(15 + slot));
+            }
+          }
+        };
+        if (n_my > 0) stream_conv(p.w1img);
+        for (int i = 0; i < n_my; ++i) {
+          if (conv2_first) {
+            stream_conv(p.w2img);
+            if (i + 1 < n_my) stream_conv(p.w1img);
+          } else {
+            if (i + 1 < n_my) stream_conv(p.w1img);
+            stream_conv(p.w2img);
+          }
+        }
+        wa.end(p.dbg, 1, L0, n_my);
       }
       if (wid < p.n_issuers) {
         WaitAcc<DBG> wa;
         wa.begin();
-        wa.wait(0, BAR(14), 0, 810);
+        if (p.w_resident) wa.wait(0, BAR(14), 0, 810);
+        int gw = 0;                                   // ring mode: taps consumed so far
         const uint32_t b_lbo = (uint32_t)NT * 32;
         const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
         const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows * 16, 128);
@@ -1491,6 +1535,27 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           const uint32_t d0 = acc + (uint32_t)wid * mt_cols;
           const uint64_t ks_step16 = (uint64_t)(2u * a_rows);
           const uint64_t lo_delta = (uint64_t)a_lo_delta16;
+          if (!p.w_resident) {      // streamed weights: tap j of this conv sits in ring slot gw % w_stages
+            uint32_t accum = 0u;
+            for (int j = 0; j < K; ++j, ++gw) {
+              const int slot = gw % p.w_stages;
+              wa.wait(0, BAR(15 + slot), (uint32_t)((gw / p.w_stages) & 1), 895 + slot);
+              tc_fence_after();
+              uint64_t bdj = b_tmpl + (uint64_t)(((w1s + (uint32_t)slot * (uint32_t)p.stage_bytes) >> 4) & 0x3FFF);
+              uint64_t ad = ad0 + (uint64_t)(j * dil);
+              for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bdj += kb_step16) {
+                uint64_t a = ad;
+                uint32_t d = d0;
+                for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) {
+                  umma_f16_elect(d, a, bdj, idesc2, accum);
+                  umma_f16_elect(d, a + lo_delta, bdj, idesc, 1u);
+                }
+                accum = 1u;
+              }
+              umma_commit_elect(BAR(19 + slot));      // the slot may be refilled once these UMMAs have read it
+            }
+            return;
+          }
           if (m_tiles <= n_iss) {   // one M tile per issuer (every plan tc3_plan makes): k-steps unrolled
             if (ksteps == 1) { issue_conv_1mt<1>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
             if (ksteps == 2) { issue_conv_1mt<2>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
@@ -1523,9 +1588,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           umma_commit_elect(BAR(4 + as));
         };
         auto conv2 = [&](int i) {
-          const int bs = i & 1;   // acc2 is double buffered: epiB(i-1) overlaps conv2(i)
+          const int bs = i % p.acc2_stages;   // acc2 double buffered (when TMEM allows): epiB(i-1) overlaps conv2(i)
           wa.wait(3, BAR(8), (uint32_t)(i & 1), 840);
-          if (i >= 2) wa.wait(4, BAR(12 + bs), (uint32_t)((i / 2 - 1) & 1), 850 + bs);
+          if (i >= p.acc2_stages) wa.wait(4, BAR(12 + bs), (uint32_t)((i / p.acc2_stages - 1) & 1), 850 + bs);
           tc_fence_after();
           run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1,
                    acc2_base + (uint32_t)(bs * p.acc_cols));
@@ -1534,8 +1599,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         };
         if (n_my > 0) conv1(0);
         for (int i = 0; i < n_my; ++i) {
-          if (i + 1 < n_my) conv1(i + 1);
-          conv2(i);
+          if (conv2_first) {
+            conv2(i);
+            if (i + 1 < n_my) conv1(i + 1);
+          } else {
+            if (i + 1 < n_my) conv1(i + 1);
+            conv2(i);
+          }
         }
         wa.end(p.dbg, 2, wid == 0 && L0, n_my);
       }
@@ -1621,7 +1691,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * p.m_out;
       {  // ---- epiB: acc2 -> +b2 + x (+ MRF accumulate) -> y
-        const int bs = it & 1;
+        const int bs = it % p.acc2_stages;
         const float* __restrict__ xb = p.x + (long long)b * C * p.L;
         float* __restrict__ yb = p.y + (long long)b * C * p.L;
         const float inv = 1.0f / p.acc_div;
@@ -1657,7 +1727,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               for (int i = 0; i < 16; ++i) xv[i] += ok ? py[(uint32_t)i * uL] : 0.f;
             }
             if (!waited) {
-              wa.wait(0, BAR(10 + bs), (uint32_t)((it >> 1) & 1), 880 + bs);
+              wa.wait(0, BAR(10 + bs), (uint32_t)((it / p.acc2_stages) & 1), 880 + bs);
               tc_fence_after();
               waited = true;
             }
@@ -1691,20 +1761,25 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 }
 
 inline size_t tc3_smem_bytes(const Tc3Args& p) {
-  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + 2ULL * p.h_rows_alloc * p.C * 2 +
-         2ULL * p.kblocks * p.C * 64 + 16 * 8;
+  const size_t w = p.w_resident ? 2ULL * p.kblocks * p.C * 64 : (size_t)p.w_stages * p.stage_bytes;
+  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + 2ULL * p.h_rows_alloc * p.C * 2 + w + 24 * 8;
 }
 
-// conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64)
+// conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64).
+// Both images resident in shared memory when they fit; otherwise (C = 64, k = 7 / 11) they are streamed through a ring,
+// one tap per slot, and the tile is made as tall as TMEM allows (single accumulator sets) because every tile re-streams
+// all 2*K taps from L2: positions per weight pass is what bounds those units.
 inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   if (C % 16 || C > 64 || K % 2 == 0) return false;
   if ((long long)C * L >= 0x7fffffffLL - 65536) return false;   // 32-bit offsets inside the utterance plane
   const int ksteps = C / 16, kblocks = K * ksteps;
   const long long BUDGET = 225 * 1024;
-  int best_m = 0, best_a1 = 0, best_acc1 = 0;
+  int best_m = 0, best_a1 = 0, best_acc1 = 0, best_acc2 = 2, best_res = 1, best_wst = 0;
   double best_sc = -1;
   static const int force_m_env = getenv("FV_TC3_M") ? atoi(getenv("FV_TC3_M")) : 0;   // tuning knob
+  static const int ring_env = getenv("FV_TC3_RING") ? atoi(getenv("FV_TC3_RING")) : 1;   // 0: never stream weights
   int force_m = force_m_env;
+  const long long stage_bytes = (long long)ksteps * C * 64;   // one tap
 retry:
   for (int acc1 = 2; acc1 >= 1; --acc1)
     for (int a1 = 2; a1 >= 1; --a1)
@@ -1723,8 +1798,24 @@ retry:
         double sc = (double)m_out / (128.0 * m) * tail;          // useful fraction of computed rows x wave balance
         sc *= (a1 == 2 ? 1.0 : 0.8) * (acc1 == 2 ? 1.0 : 0.85);  // overlap bonuses
         sc *= (m >= 2 ? 1.0 : 0.9);
-        if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; }
+        if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; best_acc2 = 2; best_res = 1; best_wst = 0; }
       }
+  if (best_sc < 0 && ring_env && stage_bytes <= 32768) {   // streamed weights
+    for (int m = 4; m >= 1 && best_sc < 0; --m) {
+      if (force_m > 0 && m != force_m) continue;
+      for (int acc = 2; acc >= 1 && best_sc < 0; --acc) {        // accumulator sets of conv1 and of conv2
+        if (2 * acc * m * 2 * C > 512) continue;
+        for (int a1 = 2; a1 >= 1 && best_sc < 0; --a1)
+          for (int wst = 4; wst >= 3; --wst) {
+            const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
+            const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + wst * stage_bytes + 256;
+            if (sm > BUDGET || 128 * m - (K - 1) <= 0) continue;
+            best_sc = 1.0; best_m = m; best_a1 = a1; best_acc1 = acc; best_acc2 = acc; best_res = 0; best_wst = wst;
+            break;
+          }
+      }
+    }
+  }
   if (best_sc < 0 && force_m > 0) { force_m = 0; goto retry; }   // forced tile count infeasible for this width
   if (best_sc < 0) return false;
   p.B = B; p.C = C; p.L = L; p.K = K; p.dil = dil;
@@ -1734,12 +1825,16 @@ retry:
   p.m_out = 128 * best_m - (K - 1);
   p.a1_stages = best_a1;
   p.acc1_stages = best_acc1;
-  p.n_issuers = std::min(best_m, TC2_ISSUE_WARPS);
+  p.acc2_stages = best_acc2;
+  p.w_resident = best_res;
+  p.w_stages = best_wst;
+  p.stage_bytes = (int)stage_bytes;
+  p.n_issuers = std::min(best_m, best_res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);   // ring mode: warp 11 is the producer
   static const int force_iss = getenv("FV_TC3_ISSUERS") ? atoi(getenv("FV_TC3_ISSUERS")) : 0;   // tuning knob
   if (force_iss > 0) p.n_issuers = std::max(1, std::min(p.n_issuers, force_iss));
   p.acc_cols = best_m * 2 * C;
   int cols = 32;
-  while (cols < (best_acc1 + 2) * p.acc_cols) cols <<= 1;
+  while (cols < (best_acc1 + best_acc2) * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.ksteps = ksteps;
   p.kblocks = kblocks;

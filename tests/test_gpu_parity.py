@@ -416,7 +416,8 @@ def test_tc_conv_transpose_shapes(Cin, Cout, k, s, Lin):
 
 
 @pytest.mark.parametrize("C,K,L", [(16, 3, 700), (16, 11, 2100), (32, 7, 1000), (32, 11, 333), (64, 3, 400),
-                                   (16, 7, 60), (48, 3, 130)])
+                                   (16, 7, 60), (48, 3, 130),
+                                   (64, 7, 900), (64, 11, 1500), (64, 11, 97), (48, 11, 700)])   # streamed-weight ring
 def test_fused_resblock1_unit_kernel(C, K, L):
     """conv1 -> LeakyReLU -> conv2 -> +x fused in one tcgen05 kernel (h stays in shared memory) vs the oracle."""
     if TC_DISABLED:
