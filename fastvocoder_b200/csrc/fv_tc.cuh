@@ -1801,8 +1801,10 @@ retry:
         if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; best_acc2 = 2; best_res = 1; best_wst = 0; }
       }
   if (best_sc < 0 && ring_env && stage_bytes <= 32768) {   // streamed weights
+    static const int ring_m_env = getenv("FV_TC3_RING_M") ? atoi(getenv("FV_TC3_RING_M")) : 0;   // tuning knob
     for (int m = 4; m >= 1 && best_sc < 0; --m) {
       if (force_m > 0 && m != force_m) continue;
+      if (ring_m_env > 0 && m != ring_m_env) continue;
       for (int acc = 2; acc >= 1 && best_sc < 0; --acc) {        // accumulator sets of conv1 and of conv2
         if (2 * acc * m * 2 * C > 512) continue;
         for (int a1 = 2; a1 >= 1 && best_sc < 0; --a1)
@@ -1899,17 +1901,18 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     if (!rep.begin(gx)) return -1;
     p.dbg = rep.dev;
     conv_tc3_fused_kernel<true><<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
-    static const char* const roles[8] = {"loader", nullptr, "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
+    static const char* const roles[8] = {"loader", "producer", "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
     static const char* const slots[8][5] = {{"a1_empty", nullptr, nullptr, nullptr, nullptr},
-                                            {nullptr, nullptr, nullptr, nullptr, nullptr},
+                                            {"w_empty", nullptr, nullptr, nullptr, nullptr},
                                             {"w_full", "a1_full", "acc1_empty", "a2_full", "acc2_empty"},
                                             {nullptr, nullptr, nullptr, nullptr, nullptr},
                                             {"acc1_full", "a2_empty", nullptr, nullptr, nullptr},
                                             {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
     char title[256];
     snprintf(title, sizeof title,
-             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d issuers=%d tiles=%d grid=%d", C,
-             K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.n_issuers, p.total_tiles, gx);
+             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d issuers=%d "
+             "tiles=%d grid=%d", C, K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
+             p.w_resident, p.w_stages, p.n_issuers, p.total_tiles, gx);
     rep.finish(st, title, roles, slots);
   } else {
     if (cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false>, p) != cudaSuccess) return -1;
