@@ -87,7 +87,7 @@ for n in ("fused_unit", "tc2_c128k11", "tc2_basis"):
           "issue active %", d[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])
     if n == "fused_unit":
         traffic.setdefault("hifigan", {})["tcgen05-fused-unit"] = {
-            "bytes_per_launch": b, "batch": 8, "launch": "fused ResBlock1 unit C=32 k=11 d=1 (L=120000)",
+            "bytes_per_launch": b, "batch": 8, "launch": "fused ResBlock1 unit C=32 k=3 d=1 (L=120000), the first stage-3 unit (tc3 launch index 9 of a forward)",
             "algorithmic_bytes": 2 * 8 * 32 * 120000 * 4}
     elif n == "tc2_c128k11":
         traffic.setdefault("hifigan", {})["tcgen05"] = {
