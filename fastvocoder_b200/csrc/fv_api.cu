@@ -228,6 +228,10 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   static const bool fuse_disabled_env = getenv("FV_NO_FUSE") != nullptr;
   const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES) && !tc_disabled_env;
   const bool fuse_ok = !fuse_disabled_env;
+  // MRF sum on the tensor-core path: 1/num_kernels folded into every branch and accumulated with red.global.add (no read of
+  // the running sum in the epilogues); the exact-fp32 path keeps the reference's add-then-divide order.  FV_MRF_RED=0: off.
+  static const bool mrf_red_env = getenv("FV_MRF_RED") == nullptr || atoi(getenv("FV_MRF_RED")) != 0;
+  const bool mrf_red = tc_ok && mrf_red_env;
   const bool pair_ok = !fuse_disabled_env;   // ResidualStack: fuse the two 1x1 convs (both kernels support two inputs)
   const int Be = eff_batch(m, B, flags);
   const size_t each = max_act_floats(m, Be, T);
@@ -345,7 +349,9 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
             float* dst = last ? s_out : (u % 2 ? bufU1 : bufU0);
             int acc = ACC_STORE;
             float div = 1.f;
-            if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
+            if (last && mrf_red && nb_br > 1) {   // 1/num_kernels folded into every branch, no read of the running sum
+              acc = (j == 0) ? ACC_STORE_SCALE : ACC_RED_SCALE; div = (float)nb_br;
+            } else if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
             if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
               if (tc_ok && fuse_ok) {   // one kernel: conv1 -> lrelu -> conv2 -> +x, h stays in shared memory
                 const Layer& la = m.layers[br.units[u].c1];

@@ -12,7 +12,16 @@ namespace fv {
 extern std::atomic<long long> g_launches;
 
 enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
-enum { ACC_STORE = 0, ACC_ADD = 1, ACC_ADD_DIV = 2 };
+// ACC_ADD / ACC_ADD_DIV: read-modify-write of the running MRF sum exactly as hifigan.py:98-103 (xs += ...; xs / num_kernels).
+// ACC_STORE_SCALE / ACC_RED_SCALE: the same sum with the 1/num_kernels folded into every branch — the first branch stores
+// v/div, the others ADD v/div with a fire-and-forget reduction (red.global.add.f32, no read of the running sum in the
+// epilogue); every element is touched by exactly one thread per launch, so the result is deterministic and differs from
+// the divide-at-the-end form by rounding only (~1e-7 relative).
+enum { ACC_STORE = 0, ACC_ADD = 1, ACC_ADD_DIV = 2, ACC_STORE_SCALE = 3, ACC_RED_SCALE = 4 };
+__host__ __device__ inline bool acc_reads_y(int m) { return m == ACC_ADD || m == ACC_ADD_DIV; }
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2 };
 
 struct ConvArgs {
@@ -165,6 +174,8 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const ConvArgs a) {
       if (rb) v += rb[o];
       if (a.acc_mode == ACC_ADD) v = yb[o] + v;
       else if (a.acc_mode == ACC_ADD_DIV) v = (yb[o] + v) / a.acc_div;
+      else if (a.acc_mode == ACC_STORE_SCALE) v = v * (1.0f / a.acc_div);
+      else if (a.acc_mode == ACC_RED_SCALE) v = yb[o] + v * (1.0f / a.acc_div);
       if (a.post_tanh) v = tanhf(v);
       yb[o] = v;
     }

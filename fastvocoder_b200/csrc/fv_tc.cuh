@@ -597,7 +597,8 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
   const int nchunks = p.NT >> 4;
   const int n_it = nchunks * p.m_tiles;          // iteration = (chunk c, M tile mt), mt fastest
   // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division, far inside 1e-4
-  const float inv = a.acc_mode == ACC_ADD_DIV ? 1.0f / a.acc_div : 1.0f;
+  const float inv = (a.acc_mode == ACC_ADD_DIV || a.acc_mode >= ACC_STORE_SCALE) ? 1.0f / a.acc_div : 1.0f;
+  const bool red = a.acc_mode == ACC_RED_SCALE;
   const int ostride = a.Lpos;   // 32-bit offsets inside the utterance plane (tc2_plan)
   const uint32_t uos = (uint32_t)ostride;
   const int row = q * 32 + lane;
@@ -633,7 +634,7 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
       for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok2) ? __ldg(pr + (uint32_t)i * uos) : 0.f;
     }
     float* py = opaque_ptr(yb + (ok ? o0 : 0));
-    if (a.acc_mode != ACC_STORE) {
+    if (acc_reads_y(a.acc_mode)) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) addend[i] += ok ? py[(uint32_t)i * uos] : 0.f;
     }
@@ -667,8 +668,13 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
           addend[4 * i4] += bv.x; addend[4 * i4 + 1] += bv.y; addend[4 * i4 + 2] += bv.z; addend[4 * i4 + 3] += bv.w;
         }
       }
+      if (red) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) py[(uint32_t)i * uos] = (__uint_as_float(rr[i]) + addend[i]) * inv;
+        for (int i = 0; i < 16; ++i) red_add_f32(py + (uint32_t)i * uos, (__uint_as_float(rr[i]) + addend[i]) * inv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) py[(uint32_t)i * uos] = (__uint_as_float(rr[i]) + addend[i]) * inv;
+      }
     }
     if (DBG) wa.w[4] += clock64() - tdbg;        // "store": bias add + issuing the 16 stores
     c = c2; mt = mt2;
@@ -809,7 +815,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
           if (pos >= a.Lpos) continue;
           const long long o = (long long)(nt * p.NT + n) * a.Lpos + pos;
           if (a.res) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.res + (long long)b * a.res_bs + o));
-          if (a.acc_mode != ACC_STORE) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + (long long)b * a.y_bs + o));
+          if (acc_reads_y(a.acc_mode)) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.y + (long long)b * a.y_bs + o));
         }
       }
     }
@@ -1080,7 +1086,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
               const double ring_bw = std::min(14.0, (double)wb / 2500.0);
               const double t_w = res ? 0.0 : (double)w_total / ring_bw;
               const double t_epi = (double)mt * 128 * NT *
-                                       (0.34 + (a.res != nullptr ? 0.47 : 0.0) + (a.acc_mode != ACC_STORE ? 0.74 : 0.0)) +
+                                       (0.34 + (a.res != nullptr ? 0.47 : 0.0) + (acc_reads_y(a.acc_mode) ? 0.74 : 0.0)) +
                                    600.0;
               const double t_core = std::max(t_mma, t_w);
               double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
@@ -1320,6 +1326,10 @@ struct Tc3Args {
   // (conv1 of tile 0, then per tile conv2(i), conv1(i+1)).  Resident mode: w_resident = 1.
   int w_resident, w_stages, stage_bytes;
   int acc2_stages;         // accumulator sets of conv2 (2 unless TMEM is needed for larger tiles)
+  // Ping-pong tiles: each tile in flight owns ONE A buffer and ONE accumulator set for both of its convs — epiA writes h
+  // in place over the (dead) x tile and conv2 accumulates over the conv1 columns epiA has drained.  Two tiles in flight
+  // with half the TMEM / no separate A2 buffer; the issuers walk pairs: conv1(a) conv1(b) conv2(a) conv2(b).
+  int pp;
   long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
@@ -1351,7 +1361,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   const uint32_t w_bytes = (uint32_t)p.kblocks * kblock_bytes;
   uint8_t* A1 = smem;                                            // [a1_stages][hi|lo]
   uint8_t* A2 = A1 + (size_t)p.a1_stages * 2 * a1_bytes;        // [hi|lo]
-  uint8_t* W1 = A2 + 2 * (size_t)a2_bytes;                      // resident: [W1 | W2]; ring: w_stages slots
+  uint8_t* W1 = A2 + (p.pp ? 0 : 2 * (size_t)a2_bytes);         // resident: [W1 | W2]; ring: w_stages slots (pp: no A2 buffer)
   uint8_t* W2 = W1 + w_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(W1 + (p.w_resident ? 2 * (size_t)w_bytes : (size_t)p.w_stages * p.stage_bytes));
   // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  [10,12) acc2_full  [12,14) acc2_empty  14 w_full
@@ -1373,7 +1383,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       mbar_init(BAR(6 + s), 4);
     }
     mbar_init(BAR(8), 4);
-    mbar_init(BAR(9), p.n_issuers);
+    mbar_init(BAR(9), p.pp ? 4 : p.n_issuers);   // pp: h_full of the odd buffer; else a2_empty
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(10 + s), p.n_issuers);
       mbar_init(BAR(12 + s), 4);
@@ -1390,7 +1400,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t acc2_base = tmem_base + (uint32_t)(p.acc1_stages * p.acc_cols);   // the acc2 set(s) follow
+  const uint32_t acc2_base = tmem_base + (uint32_t)((p.pp ? 0 : p.acc1_stages) * p.acc_cols);   // the acc2 set(s) follow (pp: aliased)
   // single-buffered A1: conv2(i) is issued before conv1(i+1) so that it never waits behind the load of the next tile
   const bool conv2_first = p.a1_stages == 1;
 
@@ -1453,7 +1463,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       if (lane == 0) mbar_arrive(BAR(0 + s));
       // epiB of this tile (two tiles from now) adds the running MRF sum y: a DRAM read its 4 warps cannot hide.
       // Pull those lines into L2 now (x itself was just read by this loop, so the residual is an L2 hit already).
-      if (p.acc_mode != ACC_STORE) {
+      if (acc_reads_y(p.acc_mode)) {
         const int lines_per_row = (p.m_out * 4 + 127) >> 7;
         const int total = C * lines_per_row;
         const float* __restrict__ yb = p.y + (long long)b * C * p.L;
@@ -1497,8 +1507,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             }
           }
         };
-        if (n_my > 0) stream_conv(p.w1img);
-        for (int i = 0; i < n_my; ++i) {
+        if (p.pp) {
+          for (int i = 0; i < n_my; i += 2) {
+            stream_conv(p.w1img);
+            if (i + 1 < n_my) stream_conv(p.w1img);
+            stream_conv(p.w2img);
+            if (i + 1 < n_my) stream_conv(p.w2img);
+          }
+        } else if (n_my > 0) stream_conv(p.w1img);
+        for (int i = 0; i < n_my && !p.pp; ++i) {
           if (conv2_first) {
             stream_conv(p.w2img);
             if (i + 1 < n_my) stream_conv(p.w1img);
@@ -1580,15 +1597,28 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         auto conv1 = [&](int i) {
           const int s = i % p.a1_stages, as = i % p.acc1_stages;
           wa.wait(1, BAR(0 + s), (uint32_t)((i / p.a1_stages) & 1), 820 + s);
-          if (i >= p.acc1_stages) wa.wait(2, BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
+          if (p.pp) {   // the set is free once epiB of the tile two back has drained it
+            if (i >= 2) wa.wait(2, BAR(12 + as), (uint32_t)((i / 2 - 1) & 1), 830 + as);
+          } else if (i >= p.acc1_stages) {
+            wa.wait(2, BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
+          }
           tc_fence_after();
           run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w1s, p.dil,
                    tmem_base + (uint32_t)(as * p.acc_cols));
-          umma_commit_elect(BAR(2 + s));
+          if (!p.pp) umma_commit_elect(BAR(2 + s));   // pp: the buffer stays busy (h in place) until conv2 is done
           umma_commit_elect(BAR(4 + as));
         };
         auto conv2 = [&](int i) {
           const int bs = i % p.acc2_stages;   // acc2 double buffered (when TMEM allows): epiB(i-1) overlaps conv2(i)
+          if (p.pp) {   // h sits in the tile's own buffer (row stride x_rows), the accumulators are the drained conv1 set
+            wa.wait(3, BAR(8 + bs), (uint32_t)((i / 2) & 1), 840 + bs);
+            tc_fence_after();
+            run_conv(a1_tmpl, smem_u32(A1 + (size_t)bs * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w2s, 1,
+                     tmem_base + (uint32_t)(bs * p.acc_cols));
+            umma_commit_elect(BAR(2 + bs));   // buffer free for the loader
+            umma_commit_elect(BAR(10 + bs));
+            return;
+          }
           wa.wait(3, BAR(8), (uint32_t)(i & 1), 840);
           if (i >= p.acc2_stages) wa.wait(4, BAR(12 + bs), (uint32_t)((i / p.acc2_stages - 1) & 1), 850 + bs);
           tc_fence_after();
@@ -1597,8 +1627,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           umma_commit_elect(BAR(9));
           umma_commit_elect(BAR(10 + bs));
         };
-        if (n_my > 0) conv1(0);
-        for (int i = 0; i < n_my; ++i) {
+        if (p.pp) {
+          for (int i = 0; i < n_my; i += 2) {
+            conv1(i);
+            if (i + 1 < n_my) conv1(i + 1);
+            conv2(i);
+            if (i + 1 < n_my) conv2(i + 1);
+          }
+        } else if (n_my > 0) conv1(0);
+        for (int i = 0; i < n_my && !p.pp; ++i) {
           if (conv2_first) {
             conv2(i);
             if (i + 1 < n_my) conv1(i + 1);
@@ -1617,6 +1654,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     const int nchunks = NT >> 4;
     uint8_t* A2_hi = A2;
     uint8_t* A2_lo = A2 + a2_bytes;
+    uint32_t h_rows = (uint32_t)p.h_rows_alloc;   // row stride of the h planes
     int it = 0;
     WaitAcc<DBG> wa;
     wa.begin();
@@ -1627,7 +1665,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       {  // ---- epiA: acc1 -> +b1 -> lrelu -> fp16 split -> A2 (zero rows outside the sequence: conv2's zero padding)
         const int as = it % p.acc1_stages;
         wa.wait(0, BAR(4 + as), (uint32_t)((it / p.acc1_stages) & 1), 860 + as);
-        if (it >= 1) wa.wait(1, BAR(9), (uint32_t)((it - 1) & 1), 870);
+        if (p.pp) {   // in place: conv1 (whose completion acc1_full signals) was the last reader of this buffer's x tile
+          A2_hi = A1 + (size_t)as * 2 * a1_bytes;
+          A2_lo = A2_hi + a1_bytes;
+          h_rows = (uint32_t)p.x_rows;
+        } else if (it >= 1) {
+          wa.wait(1, BAR(9), (uint32_t)((it - 1) & 1), 870);
+        }
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
         for (int c = 0; c < nchunks; ++c) {
@@ -1661,8 +1705,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               hp[i >> 1] &= keep;
               lp[i >> 1] &= keep;
             }
-            const uint32_t off0 = ((uint32_t)(2 * c) * p.h_rows_alloc + r) * 16;
-            const uint32_t off1 = ((uint32_t)(2 * c + 1) * p.h_rows_alloc + r) * 16;
+            const uint32_t off0 = ((uint32_t)(2 * c) * h_rows + r) * 16;
+            const uint32_t off1 = ((uint32_t)(2 * c + 1) * h_rows + r) * 16;
             *reinterpret_cast<uint4*>(A2_hi + off0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             *reinterpret_cast<uint4*>(A2_hi + off1) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
             *reinterpret_cast<uint4*>(A2_lo + off0) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
@@ -1673,8 +1717,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(BAR(6 + as));   // acc1 set drained
-          mbar_arrive(BAR(8));        // A2 ready for conv2
+          if (p.pp) {
+            mbar_arrive(BAR(8 + as));   // h ready AND the set drained: conv2 may overwrite the columns
+          } else {
+            mbar_arrive(BAR(6 + as));   // acc1 set drained
+            mbar_arrive(BAR(8));        // A2 ready for conv2
+          }
         }
       }
     }
@@ -1722,7 +1770,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             float* py = opaque_ptr(yb + (ok ? o0 : 0));
 #pragma unroll
             for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(px + (uint32_t)i * uL) : 0.f;
-            if (p.acc_mode != ACC_STORE) {   // running MRF sum: fold it into the prefetched addend (x + xs)
+            if (acc_reads_y(p.acc_mode)) {   // running MRF sum: fold it into the prefetched addend (x + xs)
 #pragma unroll
               for (int i = 0; i < 16; ++i) xv[i] += ok ? py[(uint32_t)i * uL] : 0.f;
             }
@@ -1740,12 +1788,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               v[i] = (__uint_as_float(rr[i]) + __uint_as_float(r2[i]) + bias[i]) + xv[i];
-            if (p.acc_mode == ACC_ADD_DIV) {
+            if (p.acc_mode == ACC_ADD_DIV || p.acc_mode >= ACC_STORE_SCALE) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= inv;
             }
+            if (p.acc_mode == ACC_RED_SCALE) {   // y += v / num_kernels without reading y (one thread per element)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) py[(uint32_t)i * uL] = v[i];
+              for (int i = 0; i < 16; ++i) red_add_f32(py + (uint32_t)i * uL, v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) py[(uint32_t)i * uL] = v[i];
+            }
           }
         }
         tc_fence_before();
@@ -1762,7 +1815,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 
 inline size_t tc3_smem_bytes(const Tc3Args& p) {
   const size_t w = p.w_resident ? 2ULL * p.kblocks * p.C * 64 : (size_t)p.w_stages * p.stage_bytes;
-  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + 2ULL * p.h_rows_alloc * p.C * 2 + w + 24 * 8;
+  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + (p.pp ? 0 : 2ULL * p.h_rows_alloc * p.C * 2) + w + 24 * 8;
 }
 
 // conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64).
@@ -1774,7 +1827,7 @@ inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
   if ((long long)C * L >= 0x7fffffffLL - 65536) return false;   // 32-bit offsets inside the utterance plane
   const int ksteps = C / 16, kblocks = K * ksteps;
   const long long BUDGET = 225 * 1024;
-  int best_m = 0, best_a1 = 0, best_acc1 = 0, best_acc2 = 2, best_res = 1, best_wst = 0;
+  int best_m = 0, best_a1 = 0, best_acc1 = 0, best_acc2 = 2, best_res = 1, best_wst = 0, best_pp = 0;
   double best_sc = -1;
   static const int force_m_env = getenv("FV_TC3_M") ? atoi(getenv("FV_TC3_M")) : 0;   // tuning knob
   static const int ring_env = getenv("FV_TC3_RING") ? atoi(getenv("FV_TC3_RING")) : 1;   // 0: never stream weights
@@ -1802,6 +1855,20 @@ retry:
       }
   if (best_sc < 0 && ring_env && stage_bytes <= 32768) {   // streamed weights
     static const int ring_m_env = getenv("FV_TC3_RING_M") ? atoi(getenv("FV_TC3_RING_M")) : 0;   // tuning knob
+    static const int pp_env = getenv("FV_TC3_PP") ? atoi(getenv("FV_TC3_PP")) : 1;                // 0: no ping-pong tiles
+    // ping-pong tiles first: two tiles in flight, each with one in-place A buffer and one accumulator set
+    for (int m = 4; m >= 1 && best_sc < 0 && pp_env; --m) {
+      if (force_m > 0 && m != force_m) continue;
+      if (ring_m_env > 0 && m != ring_m_env) continue;
+      if (2 * m * 2 * C > 512 || 128 * m - (K - 1) <= 0) continue;
+      for (int wst = 4; wst >= 3; --wst) {
+        const long long x_rows = 128LL * m + (long long)(K - 1) * dil;
+        const long long sm = 2 * 2 * x_rows * C * 2 + wst * stage_bytes + 256;
+        if (sm > BUDGET) continue;
+        best_sc = 1.0; best_m = m; best_a1 = 2; best_acc1 = 2; best_acc2 = 2; best_res = 0; best_wst = wst; best_pp = 1;
+        break;
+      }
+    }
     for (int m = 4; m >= 1 && best_sc < 0; --m) {
       if (force_m > 0 && m != force_m) continue;
       if (ring_m_env > 0 && m != ring_m_env) continue;
@@ -1829,6 +1896,7 @@ retry:
   p.acc1_stages = best_acc1;
   p.acc2_stages = best_acc2;
   p.w_resident = best_res;
+  p.pp = best_pp;
   p.w_stages = best_wst;
   p.stage_bytes = (int)stage_bytes;
   p.n_issuers = std::min(best_m, best_res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);   // ring mode: warp 11 is the producer
@@ -1836,7 +1904,7 @@ retry:
   if (force_iss > 0) p.n_issuers = std::max(1, std::min(p.n_issuers, force_iss));
   p.acc_cols = best_m * 2 * C;
   int cols = 32;
-  while (cols < (best_acc1 + best_acc2) * p.acc_cols) cols <<= 1;
+  while (cols < (best_pp ? 2 : best_acc1 + best_acc2) * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
   p.ksteps = ksteps;
   p.kblocks = kblocks;
@@ -1910,9 +1978,9 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
                                             {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
     char title[256];
     snprintf(title, sizeof title,
-             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d issuers=%d "
+             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d pp=%d issuers=%d "
              "tiles=%d grid=%d", C, K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
-             p.w_resident, p.w_stages, p.n_issuers, p.total_tiles, gx);
+             p.w_resident, p.w_stages, p.pp, p.n_issuers, p.total_tiles, gx);
     rep.finish(st, title, roles, slots);
   } else {
     if (cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false>, p) != cudaSuccess) return -1;
