@@ -144,3 +144,23 @@ def test_pqmf_design_is_byte_identical(specs, ops_golden):
     assert np.array_equal(p.synthesis_filter.numpy(), ops_golden["pqmf_synthesis_filter"])
     with pytest.raises(_lib.FvError):
         p.synthesis(torch.zeros(1, 4, 8))             # CPU tensor: no fallback
+
+
+def test_tile_planners_respect_hardware_limits(tmp_path):
+    """Host-only sweep (tests/native/planner_check.cu): every plan tc2_plan / tc3_plan makes for the shipped layer shapes and a
+    grid of odd ones fits shared memory / TMEM / barrier slots and is internally consistent — catches planner regressions
+    before they reach a GPU box (a bad plan there means a trap or a hang, not a test failure)."""
+    import shutil
+    import subprocess
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc) and not shutil.which("nvcc"):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "planner_check")
+    src = os.path.join(REPO, "tests", "native", "planner_check.cu")
+    r = subprocess.run([nvcc if os.path.exists(nvcc) else "nvcc", "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-diag-suppress", "177", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    env = {k: v for k, v in os.environ.items() if not k.startswith("FV_")}
+    r = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "failures: 0" in r.stdout
