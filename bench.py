@@ -363,6 +363,13 @@ def main():
                 "shape": f"B={Bq}, sub-bands 4 x {Lq}, L2 flushed before each run, best of 5",
             }
         del xs, xw, wav
+        for r in profile_rows:                        # the generator's own narrow output conv (conv_post / LastLayer)
+            if r["N"] <= 4 and r["ms"] > 0:
+                gbs = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+                hbm_kernels["output_conv"] = {"layer": r["name"], "kernel": r["kernel"], "Cin": r["Cin"], "N": r["N"], "K": r["K"],
+                                              "ms": r["ms"], "GB/s": gbs, "frac_of_hbm_peak": gbs / peaks["hbm_gbs"],
+                                              "algorithmic_bytes": r["bytes"],
+                                              "note": "timed inside the step's per-layer profile (no L2 flush: input is the previous layer's output)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -------------------------------------------------------
     cpu_baseline = None

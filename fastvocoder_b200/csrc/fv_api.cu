@@ -169,6 +169,14 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   static const bool tc_disabled = getenv("FV_DISABLE_TC") != nullptr;  // operational kill switch
   // zero-padded-N layers (N < 16) have no residual / accumulate support in the masked epilogue
   const bool padded_ok = !tcl || tcl->n_pad == l.N || (c.res == nullptr && c.acc_mode == ACC_STORE);
+  static const bool narrow7_env = getenv("FV_NARROW7") == nullptr || atoi(getenv("FV_NARROW7")) != 0;
+  // HBM-bound k = 7 single-channel output convs (conv_post 16->1, LastLayer 32->1): the streaming kernel on both paths
+  // (measured 0.305 -> 0.148 ms / 0.457 -> 0.265 ms = 3.5-3.8 TB/s).  The 64->4 conv_post of Multiband-HiFi-GAN is FMA-bound
+  // there (0.56 ms) and stays on tcgen05 (0.47 ms) when tensor cores are allowed.
+  if (narrow7_env && conv_narrow7_ok(a) && (a.N <= 2 || !(c.allow_tc && !tc_disabled && tcl && tcl->eligible))) {
+    FV_CUDA(launch_conv_narrow7(a, st));
+    return FV_OK;
+  }
   if (c.allow_tc && !tc_disabled && tcl && tcl->eligible && padded_ok) {
     int rc = launch_conv_tc2(a, *tcl, st);
     if (rc == 0) {

@@ -300,6 +300,111 @@ inline bool conv_narrow_v4_ok(const ConvArgs& a) {
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
 }
 
+// Streaming kernel for the k = 7 narrow-output convs every config ends with (conv_post 16->1 / 64->4, MelGAN LastLayer
+// 32->1; padding 3, dilation 1): 4*Cin bytes in and 4*Cout bytes out per position, so HBM is the roofline.  Each thread
+// produces 4 consecutive positions from three aligned 16-byte loads per input channel (window t0-4 .. t0+7, all indices
+// compile-time -> registers), the 7*NOUT weights of the channel come from shared memory as broadcast 16-byte reads, and
+// tiles that touch the padding / the ragged end take the scalar path of conv_narrow_kernel's arithmetic.
+template <int NOUT>
+__global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
+  constexpr int K = 7, PADL = 3;
+  extern __shared__ __align__(16) float smem[];   // [Cin][NOUT][8] (tap 7 = 0)
+  for (int i = threadIdx.x; i < a.Cin * NOUT * 8; i += blockDim.x) {
+    const int j = i & 7, n = (i >> 3) % NOUT, ci = i / (8 * NOUT);
+    smem[i] = (j < K && n < a.N) ? __ldg(a.w + ((long long)ci * K + j) * a.N + n) : 0.f;   // derived image is [Cin][K][N]
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
+  float* __restrict__ yb = a.y + (long long)b * a.y_bs;
+  const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;
+  const int nquads = (a.Lpos + 3) >> 2;
+  const float slope = a.pre_slope;
+  const uint32_t uL = (uint32_t)a.Lin;
+  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < nquads; qd += gridDim.x * blockDim.x) {
+    const int t0 = qd << 2;
+    float acc[NOUT][4];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[n][q] = 0.f;
+    if (t0 - 4 >= 0 && t0 + 8 <= Lb && t0 + 4 <= a.Lpos) {   // interior: the whole 12-sample window is real data
+      const float* px = xb + t0;
+#pragma unroll 2
+      for (int ci = 0; ci < a.Cin; ++ci) {
+        const float4* xr = reinterpret_cast<const float4*>(px + (uint32_t)ci * uL);
+        const float4 v0 = __ldg(xr - 1), v1 = __ldg(xr), v2 = __ldg(xr + 1);
+        float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+        for (int i = 1; i < 11; ++i) w[i] = pre_act(w[i], slope);   // w[0], w[11] are never used (window t0-3 .. t0+6)
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          const float4 c0 = *reinterpret_cast<const float4*>(smem + (ci * NOUT + n) * 8);
+          const float4 c1 = *reinterpret_cast<const float4*>(smem + (ci * NOUT + n) * 8 + 4);
+          const float cw[7] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[n][q] = fmaf(cw[j], w[q + j + (4 - PADL)], acc[n][q]);
+        }
+      }
+    } else {   // padding / ragged end / tail: scalar taps with the generic index rules
+      for (int ci = 0; ci < a.Cin; ++ci) {
+        const float* xr = xb + (long long)ci * a.Lin;
+        for (int j = 0; j < K; ++j) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            int g = t0 + q - PADL + j;
+            if (a.pad_mode == PAD_REFLECT) {
+              if (g < 0) g = -g;
+              if (g >= Lb) g = 2 * (Lb - 1) - g;
+            }
+            const float xv = (g >= 0 && g < Lb) ? pre_act(__ldg(xr + g), slope) : 0.f;
+#pragma unroll
+            for (int n = 0; n < NOUT; ++n) acc[n][q] = fmaf(smem[(ci * NOUT + n) * 8 + j], xv, acc[n][q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      if (n >= a.N) break;
+      const float bv = a.bias ? __ldg(a.bias + n) : 0.f;
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o[q] = acc[n][q] + bv;
+        if (a.post_tanh) o[q] = tanhf(o[q]);
+      }
+      float* yo = yb + (long long)n * a.Lpos + t0;
+      if (t0 + 4 <= a.Lpos) {
+        *reinterpret_cast<float4*>(yo) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        for (int q = 0; q < 4 && t0 + q < a.Lpos; ++q) yo[q] = o[q];
+      }
+    }
+  }
+}
+// shapes the streaming kernel takes (both the tensor-core and the exact-fp32 path route them here: an HBM-bound op gains
+// nothing from a zero-padded N = 16 UMMA)
+inline bool conv_narrow7_ok(const ConvArgs& a) {
+  return a.cin_split == 0 && a.N <= 4 && a.K == 7 && a.dil == 1 && a.pad_left == 3 && a.out_layout == OUT_BCL &&
+         a.res == nullptr && a.acc_mode == ACC_STORE && a.Lpos == a.Lin && a.Lin % 4 == 0 && a.x_bs % 4 == 0 && a.y_bs % 4 == 0 &&
+         (long long)a.Cin * a.Lin < 0x7fffffffLL && (size_t)a.Cin * 4 * 8 * sizeof(float) <= 40 * 1024 &&
+         (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
+}
+inline cudaError_t launch_conv_narrow7(const ConvArgs& a, cudaStream_t st) {
+  long long g4 = ((a.Lpos + 3) / 4 + 255) / 256;
+  if (g4 > 148 * 16) g4 = 148 * 16;
+  if (g4 < 1) g4 = 1;
+  dim3 grid((unsigned)g4, a.B);
+  if (a.N == 1) conv_narrow7_kernel<1><<<grid, 256, (size_t)a.Cin * 1 * 8 * sizeof(float), st>>>(a);
+  else if (a.N == 2) conv_narrow7_kernel<2><<<grid, 256, (size_t)a.Cin * 2 * 8 * sizeof(float), st>>>(a);
+  else conv_narrow7_kernel<4><<<grid, 256, (size_t)a.Cin * 4 * 8 * sizeof(float), st>>>(a);
+  g_launches++;
+  return cudaGetLastError();
+}
+
 inline bool conv_narrow_ok(const ConvArgs& a) {
   return a.cin_split == 0 && a.N <= 4 && a.K <= 16 && a.out_layout == OUT_BCL && a.res == nullptr && a.acc_mode == ACC_STORE &&
          (size_t)a.Cin * a.K * 4 * sizeof(float) <= 40 * 1024;
@@ -328,6 +433,7 @@ inline size_t conv_ffma_smem(int co_t, int K, int dil) {
 }
 
 inline cudaError_t launch_conv_ffma(const ConvArgs& a, cudaStream_t st) {
+  if (conv_narrow7_ok(a)) return launch_conv_narrow7(a, st);
   if (conv_narrow_ok(a)) return launch_conv_narrow(a, st);
   const int co_t = a.N <= 16 ? 16 : (a.N <= 32 ? 32 : 64);
   const size_t smem = conv_ffma_smem(co_t, a.K, a.dil);
