@@ -316,7 +316,9 @@ def main():
             "passes": 3 if is_tc else 1,
             "executed_mma_frac": (3 * achieved_tf / peak_tf) if is_tc else None,
             "share_of_step": d["ms"] / total_ms, "launches_per_step": d["launches"],
-            "avg_launch_ms": d["ms"] / d["launches"], "traffic": traffic,
+            "avg_launch_ms": d["ms"] / d["launches"],
+            # DRAM bytes of ONE launch of that kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum), or null
+            "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_unit": "B/launch", "traffic_detail": traffic,
             "all_tensor_core_kernels": {"tflops": tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else None,
                                         "frac": (tc_fl / (tc_ms * 1e-3) / 1e12 / peak_tf) if tc_ms else None,
                                         "share_of_step": tc_ms / total_ms},
