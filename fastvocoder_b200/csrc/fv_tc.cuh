@@ -1853,9 +1853,30 @@ retry:
         sc *= (m >= 2 ? 1.0 : 0.9);
         if (sc > best_sc) { best_sc = sc; best_m = m; best_a1 = a1; best_acc1 = acc1; best_acc2 = 2; best_res = 1; best_wst = 0; }
       }
+  // FV_TC3_PP: 0 = no ping-pong tiles, 1 = streamed-weight units only, 2 = also resident units with k >= 7 (default),
+  // 3 = every resident unit
+  static const int pp_env = getenv("FV_TC3_PP") ? atoi(getenv("FV_TC3_PP")) : 2;
+  if (best_sc >= 0 && (pp_env >= 3 || (pp_env == 2 && K >= 7))) {
+    // Resident weights + ping-pong tiles: the same two tiles in flight need half the TMEM and no A2 buffer, so the tile can be
+    // taller (C=32: m 2 -> 4, C=16: m 3-4 -> 8): less conv2 halo recompute and fewer per-tile hand-offs.  Measured in one call
+    // (gpurun_out/pp2_*): C=32 k=11 0.676 -> 0.60 ms, C=16 k=11 0.61 -> 0.52, k=7 -3 %, k=3 +-3 % (left on the old plans);
+    // HiFi-GAN step 17.17 -> 16.88 ms.
+    static const int pp_m_env = getenv("FV_TC3_PP_M") ? atoi(getenv("FV_TC3_PP_M")) : 0;
+    for (int m = 8; m > best_m; --m) {
+      if (pp_m_env > 0 && m > pp_m_env) continue;
+      if (2 * m * 2 * C > 512) continue;
+      const long long x_rows = 128LL * m + (long long)(K - 1) * dil;
+      const long long sm = 2 * 2 * x_rows * C * 2 + 2LL * kblocks * C * 64 + 256;
+      if (sm > BUDGET) continue;
+      const int m_out = 128 * m - (K - 1);
+      const long long tiles = (long long)((L + m_out - 1) / m_out) * B;
+      if (tiles < 148 * 4) continue;            // keep enough tiles per CTA for the two-tile pipeline to fill
+      best_m = m; best_a1 = 2; best_acc1 = 2; best_acc2 = 2; best_res = 1; best_wst = 0; best_pp = 1;
+      break;
+    }
+  }
   if (best_sc < 0 && ring_env && stage_bytes <= 32768) {   // streamed weights
     static const int ring_m_env = getenv("FV_TC3_RING_M") ? atoi(getenv("FV_TC3_RING_M")) : 0;   // tuning knob
-    static const int pp_env = getenv("FV_TC3_PP") ? atoi(getenv("FV_TC3_PP")) : 1;                // 0: no ping-pong tiles
     // ping-pong tiles first: two tiles in flight, each with one in-place A buffer and one accumulator set
     for (int m = 4; m >= 1 && best_sc < 0 && pp_env; --m) {
       if (force_m > 0 && m != force_m) continue;
