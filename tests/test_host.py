@@ -164,3 +164,47 @@ def test_tile_planners_respect_hardware_limits(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "failures: 0" in r.stdout
+
+
+def test_switch_error_conventions(specs):
+    """Non-default switches: accepted where the reference class accepts them, rejected (loudly) where it does not."""
+    cfg = dict(specs["melgan-original"]["config"])
+    cfg["use_causal_conv"] = True
+    build_generator("melgan", cfg)                                   # causal MelGAN with an odd kernel is wired
+    cfg["kernel_size"] = 6
+    with pytest.raises(NotImplementedError):                         # melgan.py:68-71 changes the sequence length
+        build_generator("melgan", cfg)
+    h = dict(specs["hifigan-light"]["config"])
+    h["transposedconv"] = False
+    m = build_generator("hifigan", h)                                # UpsampleLayer: k = upsample_kernel_sizes[i], padding k // 2
+    assert m.out_length(24) > 240 * 24                                # u*L + 1 per stage (even kernels)
+    bad = _lib.FvConfig()
+    bad.kind = _lib.FV_HIFIGAN
+    bad.in_channels = 80
+    bad.num_upsamples = 1
+    bad.upsample_rates[0] = 2
+    bad.upsample_kernel_sizes[0] = 4
+    bad.channels[0] = 32
+    bad.channels[1] = 16
+    bad.pre_kernel_size = 7
+    bad.use_causal_conv = 1                                          # a MelGAN-family switch on a HiFi-GAN config
+    hd = C.c_void_p()
+    assert _lib.lib().fv_create(C.byref(bad), C.byref(hd)) != 0
+    assert b"use_causal_conv" in _lib.lib().fv_last_error()
+    b = dict(specs["basis-melgan-light"]["config"])
+    b["lastlinear"] = True
+    b["out_channels"] = 64
+    mb = build_generator("basis-melgan", b)
+    keys = set(mb.state_dict())
+    assert any(k.endswith("bn_1.running_var") for k in keys) and any(k.endswith("linear_2.weight_g") for k in keys)
+
+
+def test_variant_output_lengths(specs):
+    """UpsampleLayer changes the length law: Conv1d(k, padding k // 2) on the stretched signal gives u*L + 1 for even k."""
+    g = np.load(os.path.join(GOLDEN, "model_hifigan-light-upsamplelayer.npz"))
+    h = dict(specs["hifigan-light-upsamplelayer"]["config"])
+    m = build_generator("hifigan", h)
+    assert m.out_length(g["mel"].shape[-1]) == g["forward0_f32"].shape[-1]
+    g = np.load(os.path.join(GOLDEN, "model_multiband-hifigan-light-upsamplelayer.npz"))
+    m = build_generator("multiband-hifigan", dict(specs["multiband-hifigan-light-upsamplelayer"]["config"]))
+    assert m.out_length(g["mel"].shape[-1]) == g["forward0_f32"].shape[-1]
