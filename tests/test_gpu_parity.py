@@ -435,8 +435,7 @@ def test_fused_resblock1_unit_kernel(C, K, L):
     b1 = [dev(params[f"rb.convs1.{i}.bias"]) for i in range(3)]
     w2 = [dev(params[f"rb.convs2.{i}.weight"]) for i in range(3)]
     b2 = [dev(params[f"rb.convs2.{i}.bias"]) for i in range(3)]
-    dilc = (C.c_int * 3)(*dil) if False else None
-    import ctypes
+    import ctypes                              # `C` is the channel count in this test
     dilc = (ctypes.c_int * 3)(*dil)
     y = torch.empty(B, C, L, device="cuda")
     scratch = torch.empty(2 * B * C * L, device="cuda")
