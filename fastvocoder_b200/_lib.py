@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libfastvocoder_b200.so")
+# FV_LIB=<path>: load an experimental variant built with `python -m fastvocoder_b200.build -D... --out <path>` (A/B runs)
+LIB_PATH = os.environ.get("FV_LIB") or os.path.join(_HERE, "_C", "libfastvocoder_b200.so")
 
 FV_MAX_STAGES, FV_MAX_BRANCH, FV_MAX_DIL = 8, 8, 8
 FV_HIFIGAN, FV_MB_HIFIGAN, FV_MELGAN, FV_BASIS_MELGAN = 0, 1, 2, 3

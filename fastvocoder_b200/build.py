@@ -26,19 +26,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
-    os.makedirs(OUT_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, defs=None, out: str | None = None) -> str:
+    """Default: the in-tree library.  `defs` (e.g. ["-DFV_PACKED_F32=1"]) + `out` build an experimental variant next to it;
+    load it with FV_LIB=<path> (fastvocoder_b200/_lib.py) to A/B two binaries inside one GPU call."""
+    if out is None and not defs:
+        if not force and not _stale():
+            return OUT
+    target = out or OUT
+    os.makedirs(os.path.dirname(target), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + list(defs or []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + SOURCES
     r = subprocess.run(cmd, cwd=SRC_DIR, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    argv = sys.argv[1:]
+    defs = [a for a in argv if a.startswith("-D")]
+    out = argv[argv.index("--out") + 1] if "--out" in argv else None
+    print(build(force="--force" in argv, verbose="-v" in argv, defs=defs, out=out))

@@ -259,6 +259,30 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi2, u
 // LeakyReLU for slopes known to lie in [0, 1] (the fused-unit kernel: always an activation): one FMUL + one FMNMX
 __device__ __forceinline__ float lrelu01(float v, float slope) { return fmaxf(v, v * slope); }
 
+// EXPERIMENTAL, compile-time opt-in (-DFV_PACKED_F32=1, see fastvocoder_b200/build.py --defs): the epilogue / loader
+// arithmetic on packed fp32 pairs (FADD2 / FMUL2 / FFMA2, sm_100a).  Every packed operation is the same IEEE rn operation on
+// each half, in the same order as the scalar code, so results are bit-identical; the point is fewer issue slots per element
+// in the instruction-bound epilogues.  Not yet timed on hardware (round 2): the default build does not contain it.
+#ifndef FV_PACKED_F32
+#define FV_PACKED_F32 0
+#endif
+#if FV_PACKED_F32
+// (a + b) + c on two lanes
+__device__ __forceinline__ float2 add3_x2(float a0, float a1, float b0, float b1, float c0, float c1) {
+  return __fadd2_rn(__fadd2_rn(make_float2(a0, a1), make_float2(b0, b1)), make_float2(c0, c1));
+}
+// LeakyReLU (slope in [0, 1]) + hi/lo fp16 split of a pair: FMUL2, 2 FMNMX, 2 LOP3, FFMA2 (x - hi), 2 F2FP
+__device__ __forceinline__ void lrelu_split_x2(float2 v, float slope, uint32_t& hi2, uint32_t& lo2) {
+  const float2 m = __fmul2_rn(v, make_float2(slope, slope));
+  const float x0 = fmaxf(v.x, m.x), x1 = fmaxf(v.y, m.y);
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  const float2 l = __ffma2_rn(make_float2(h0, h1), make_float2(-1.f, -1.f), make_float2(x0, x1));   // x - h, exact
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(h1), "f"(h0));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(l.y), "f"(l.x));
+}
+#endif
+
 // Materialise a base pointer so that `base + int_index` becomes one IMAD.WIDE (the compiler otherwise re-associates
 // the 64-bit element offsets of the whole expression: five integer instructions per global access).
 template <class T>
@@ -1699,9 +1723,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             const uint32_t keep = inside ? 0xffffffffu : 0u;   // rows outside the sequence are conv2's zero padding
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
+#if FV_PACKED_F32
+              lrelu_split_x2(add3_x2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]), __uint_as_float(r2[i]),
+                                     __uint_as_float(r2[i + 1]), b1v[i], b1v[i + 1]),
+                             p.slope, hp[i >> 1], lp[i >> 1]);
+#else
               const float v0 = __uint_as_float(rr[i]) + __uint_as_float(r2[i]) + b1v[i];
               const float v1 = __uint_as_float(rr[i + 1]) + __uint_as_float(r2[i + 1]) + b1v[i + 1];
               split_f16x2(lrelu01(v0, p.slope), lrelu01(v1, p.slope), hp[i >> 1], lp[i >> 1]);
+#endif
               hp[i >> 1] &= keep;
               lp[i >> 1] &= keep;
             }
@@ -1785,6 +1815,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             tmem_ld16(tcol + (uint32_t)NT, r2);
             if (!ok) continue;
             float v[16];
+#if FV_PACKED_F32
+            const bool scaled = p.acc_mode == ACC_ADD_DIV || p.acc_mode >= ACC_STORE_SCALE;
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float2 t = __fadd2_rn(add3_x2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1]), __uint_as_float(r2[i]),
+                                            __uint_as_float(r2[i + 1]), bias[i], bias[i + 1]),
+                                    make_float2(xv[i], xv[i + 1]));
+              if (scaled) t = __fmul2_rn(t, make_float2(inv, inv));
+              v[i] = t.x; v[i + 1] = t.y;
+            }
+#else
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               v[i] = (__uint_as_float(rr[i]) + __uint_as_float(r2[i]) + bias[i]) + xv[i];
@@ -1792,6 +1833,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= inv;
             }
+#endif
             if (p.acc_mode == ACC_RED_SCALE) {   // y += v / num_kernels without reading y (one thread per element)
 #pragma unroll
               for (int i = 0; i < 16; ++i) red_add_f32(py + (uint32_t)i * uL, v[i]);
