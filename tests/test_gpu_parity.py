@@ -296,6 +296,30 @@ def test_full_size_utterance_against_cpu_port(specs):
         assert np.isfinite(y).all() and np.abs(y).max() > 0.05
 
 
+def test_baseline_config0_and_config3_sizes_against_cpu_port(specs):
+    """BASELINE.json configs[0] (MelGAN, one 80 x 200 mel) and configs[3] (Multiband-HiFi-GAN light, T = 1000, sub-bands and
+    PQMF waveform) at their full sizes vs the ATen port of the reference's CPU path."""
+    name, cfg = specs["melgan-original"]["model_name"], specs["melgan-original"]["config"]
+    m = make_model(specs, "melgan-original")
+    mel = synth_mel(1, 200, seed=11)
+    w = P.to_torch(folded_weights(specs, "melgan-original"))
+    with torch.no_grad():
+        want = P.FORWARD[name](w, cfg, torch.from_numpy(mel)).numpy()
+        y = m(dev(mel)).cpu().numpy()
+    assert y.shape == (1, 48000) and np.abs(y - want).max() < TOL
+    name, cfg = specs["multiband-hifigan-light"]["model_name"], specs["multiband-hifigan-light"]["config"]
+    m = make_model(specs, "multiband-hifigan-light")
+    mel = synth_mel(2, 1000, seed=12)
+    w = P.to_torch(folded_weights(specs, "multiband-hifigan-light"))
+    with torch.no_grad():
+        sub_want = P.FORWARD[name](w, cfg, torch.from_numpy(mel[:1]))
+        wav_want = P.pqmf_synthesis(sub_want).numpy()
+        sub, wav = m(dev(mel), synthesize=True)          # the call bench.py times for configs[3]
+    assert tuple(sub.shape) == (2, 4, 60000) and tuple(wav.shape) == (2, 1, 240000)
+    assert np.abs(sub[:1].cpu().numpy() - sub_want.numpy()).max() < TOL
+    assert np.abs(wav[:1].cpu().numpy() - wav_want).max() < 2 * TOL   # synthesis sums 4 bands with gain 4 (|wav| ~ 3)
+
+
 def test_basis_forward_equals_inference_minus_zero_inference(specs):
     """forward() == inference(mel) - inference(zeros), truncated: the identity bin/test.py:85-90 relies on."""
     m = make_model(specs, "basis-melgan-light")
