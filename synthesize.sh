@@ -1,17 +1,20 @@
-#!/bin/bash
-# usage: bash synthesize.sh <checkpoint> <mel.npy> <out.wav> <model_name> <config.yaml>
-# Same positional contract as the reference's synthesize.sh, but runs on the GPU (the reference pins CPU).
-checkpoint=$1
-mel_path=$2
-wav_path=$3
-model_name=$4
-config=$5
-
-export MODE=synthesize
-
-python3 bin/launcher.py \
-    --checkpoint_path "$checkpoint" \
-    --mel_path "$mel_path" \
-    --wav_path "$wav_path" \
-    --model_name "$model_name" \
-    --config "$config"
+#!/usr/bin/env bash
+# mel (.npy) -> wav on the GPU through the B200-native generator path.
+#
+#   bash synthesize.sh <checkpoint> <mel.npy> <out.wav> <model_name> <config.yaml>
+#
+# Five positional arguments in the order FastVocoder users already pass them; model_name is one of
+# melgan | hifigan | multiband-hifigan | basis-melgan.  Needs a CUDA device (there is no CPU path here).
+set -euo pipefail
+if [[ $# -ne 5 ]]; then
+  sed -n '2,7p' "$0" >&2
+  exit 2
+fi
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+names=(checkpoint_path mel_path wav_path model_name config)
+args=()
+for i in "${!names[@]}"; do
+  j=$((i + 1))
+  args+=("--${names[$i]}" "${!j}")
+done
+MODE=synthesize exec python3 "$here/bin/launcher.py" "${args[@]}"
