@@ -134,6 +134,13 @@ def run_reference(args, rank, world):
     ypath, B, T, label = WORKLOADS[name]
     T = args.frames or T
     cfg = load_yaml(ypath)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank when N > 1; the reference arm must still use all host threads it can
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    if torch.get_num_threads() < avail and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        torch.set_num_threads(avail)
     from fastvocoder_b200 import build_generator
     model = build_generator(name, cfg)
     weights = {k: v.numpy() for k, v in synthetic_weights(model).items()}
