@@ -161,9 +161,12 @@ def test_tile_planners_respect_hardware_limits(tmp_path):
                         "-diag-suppress", "177", "-o", exe, src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     env = {k: v for k, v in os.environ.items() if not k.startswith("FV_")}
-    r = subprocess.run([exe], capture_output=True, text=True, env=env)
-    assert r.returncode == 0, r.stdout[-3000:]
-    assert "failures: 0" in r.stdout
+    variants = [{}, {"FV_TC3_PP": "0"}, {"FV_TC3_PP": "1"}, {"FV_TC3_PP": "3"}, {"FV_TC3_RING": "0"},
+                {"FV_LOADER_FLAT": "2"}, {"FV_A_REUSE": "1"}, {"FV_TC3_RING_M": "1"}]     # every planner knob
+    for extra in variants:
+        r = subprocess.run([exe], capture_output=True, text=True, env=dict(env, **extra))
+        assert r.returncode == 0, (extra, r.stdout[-3000:])
+        assert "failures: 0" in r.stdout, extra
 
 
 def test_switch_error_conventions(specs):
