@@ -317,11 +317,20 @@ def _fill_hifi(cfg, kind, resblock_kernel_sizes, upsample_rates, upsample_initia
     cfg.post_kernel_size = 7
     cfg.out_channels = out_channels
     cfg.num_kernels = len(resblock_kernel_sizes)
-    cfg.resblock_type = 1 if str(resblock_type) == "1" else 2
+    # hifigan.py:28: `ResBlock1 if resblock_type == '1' else ResBlock2` — the reference's own comparison, so an unquoted
+    # YAML 1 (int) selects ResBlock2 exactly as it does there.
+    cfg.resblock_type = 1 if resblock_type == '1' else 2
     _set_arr(cfg.resblock_kernel_sizes, resblock_kernel_sizes)
+    if len(resblock_dilation_sizes) < len(resblock_kernel_sizes):
+        raise ValueError("resblock_dilation_sizes needs one entry per resblock kernel size")
+    # ResBlock1 hard-codes three (convs1, convs2) pairs from dilation[0..2], ResBlock2 two convs from dilation[0..1]
+    # (modules.py:190-251) whatever the list length: extra entries are ignored, missing ones raise IndexError there.
+    n_convs = 3 if cfg.resblock_type == 1 else 2
     for j, dils in enumerate(resblock_dilation_sizes[: len(resblock_kernel_sizes)]):
-        cfg.resblock_num_dilations[j] = len(dils)
-        _set_arr(cfg.resblock_dilations[j], dils)
+        if len(dils) < n_convs:
+            raise IndexError("tuple index out of range")   # what dilation[n] raises in the reference constructor
+        cfg.resblock_num_dilations[j] = n_convs
+        _set_arr(cfg.resblock_dilations[j], dils[:n_convs])
     cfg.use_final_activation = 1
     return cfg
 

@@ -99,8 +99,9 @@ def get_padding(kernel_size, dilation=1):
 
 
 def resblock1(x, params, prefix, kernel_size, dilations):
-    """ResBlock1.forward, modules.py:223-230."""
-    for i, d in enumerate(dilations):
+    """ResBlock1.forward, modules.py:223-230.  The constructor (modules.py:190-221) hard-codes THREE (convs1, convs2)
+    pairs built from dilation[0..2], whatever the length of the list (shorter: IndexError, longer: ignored)."""
+    for i, d in enumerate((dilations[0], dilations[1], dilations[2])):
         xt = leaky_relu(x, LRELU_SLOPE)
         xt = conv1d(xt, params[f"{prefix}.convs1.{i}.weight"], params[f"{prefix}.convs1.{i}.bias"],
                     dilation=d, padding=get_padding(kernel_size, d))
@@ -112,8 +113,9 @@ def resblock1(x, params, prefix, kernel_size, dilations):
 
 
 def resblock2(x, params, prefix, kernel_size, dilations):
-    """ResBlock2.forward, modules.py:247-252."""
-    for i, d in enumerate(dilations):
+    """ResBlock2.forward, modules.py:247-252.  The constructor (modules.py:233-245) hard-codes TWO convs from
+    dilation[0..1], whatever the length of the list."""
+    for i, d in enumerate((dilations[0], dilations[1])):
         xt = leaky_relu(x, LRELU_SLOPE)
         xt = conv1d(xt, params[f"{prefix}.convs.{i}.weight"], params[f"{prefix}.convs.{i}.bias"],
                     dilation=d, padding=get_padding(kernel_size, d))
@@ -274,7 +276,7 @@ def _hifigan_trunk(params, cfg, x):
     rks = cfg["resblock_kernel_sizes"]
     rds = cfg["resblock_dilation_sizes"]
     num_kernels = len(rks)
-    rb = resblock1 if str(cfg.get("resblock_type", "1")) == "1" else resblock2
+    rb = resblock1 if cfg.get("resblock_type", "1") == '1' else resblock2   # hifigan.py:28, the reference's comparison
     x = conv1d(x, params["conv_pre.weight"], params.get("conv_pre.bias"), padding=3)
     for i, (u, k) in enumerate(zip(rates, ksz)):
         x = leaky_relu(x, LRELU_SLOPE)

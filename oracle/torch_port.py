@@ -29,8 +29,8 @@ def get_padding(kernel_size, dilation=1):  # modules.py:186
     return int((kernel_size * dilation - dilation) / 2)
 
 
-def resblock1(x, params, prefix, k, dils):  # modules.py:223-230
-    for i, d in enumerate(dils):
+def resblock1(x, params, prefix, k, dils):  # modules.py:190-230 (three pairs hard-coded from dilation[0..2])
+    for i, d in enumerate((dils[0], dils[1], dils[2])):
         xt = F.leaky_relu(x, LRELU_SLOPE)
         xt = F.conv1d(xt, params[f"{prefix}.convs1.{i}.weight"], _p(params, f"{prefix}.convs1.{i}.bias"),
                       dilation=d, padding=get_padding(k, d))
@@ -41,8 +41,8 @@ def resblock1(x, params, prefix, k, dils):  # modules.py:223-230
     return x
 
 
-def resblock2(x, params, prefix, k, dils):  # modules.py:247-252
-    for i, d in enumerate(dils):
+def resblock2(x, params, prefix, k, dils):  # modules.py:233-252 (two convs hard-coded from dilation[0..1])
+    for i, d in enumerate((dils[0], dils[1])):
         xt = F.leaky_relu(x, LRELU_SLOPE)
         xt = F.conv1d(xt, params[f"{prefix}.convs.{i}.weight"], _p(params, f"{prefix}.convs.{i}.bias"),
                       dilation=d, padding=get_padding(k, d))
@@ -124,7 +124,7 @@ def pqmf_analysis(x, subbands=4, taps=62):  # pqmf.py:108-119
 def _hifigan_trunk(params, cfg, x):  # hifigan.py:92-106 / multiband_hifigan.py:101-116
     rks, rds = cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]
     nk = len(rks)
-    rb = resblock1 if str(cfg.get("resblock_type", "1")) == "1" else resblock2
+    rb = resblock1 if cfg.get("resblock_type", "1") == '1' else resblock2   # hifigan.py:28
     x = F.conv1d(x, params["conv_pre.weight"], _p(params, "conv_pre.bias"), padding=3)
     for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
         x = F.leaky_relu(x, LRELU_SLOPE)
