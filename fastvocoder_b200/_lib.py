@@ -51,7 +51,9 @@ class FvConfig(C.Structure):
         ("upsample_layer", C.c_int32),
         ("use_causal_conv", C.c_int32),
         ("lastlinear", C.c_int32),
-        ("reserved", C.c_int32 * 5),
+        ("negative_slope_set", C.c_int32),
+        ("negative_slope", C.c_float),
+        ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -88,6 +90,7 @@ SIGNATURES = {
     "fv_conv_transpose1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     "fv_resblock1": (_I, [_P, _PP, _PP, _PP, _PP, C.POINTER(_I), _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "fv_residual_stack": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "fv_basis_signal": (_I, [_P, _P, _I, _I, _P, _I, _P]),
     "fv_overlap_add": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "fv_pqmf_synthesis": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "fv_pqmf_analysis": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

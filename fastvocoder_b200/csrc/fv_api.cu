@@ -100,7 +100,12 @@ struct LayerCall {
   const float* x2 = nullptr;   // L_PAIR: second input (the un-activated stack input for the skip layer)
   float pre_slope2 = -1.f;
   const int* lens = nullptr;   // ragged batches: valid input length per utterance (device), or nullptr
+  // ConvTranspose / UpsampleLayer only: write the output LeakyReLU(out_slope)-activated in the split activation format
+  // (fv_tma.cuh) instead of fp32.  Tensor-core kernel only: run_layer returns FV_NOT_APPLICABLE when it cannot.
+  bool out_split = false;
+  float out_slope = 0.f;
 };
+constexpr int FV_NOT_APPLICABLE = 1;   // positive: not an error, the caller takes its fallback
 
 static long long layer_out_len(const Layer& l, long long Lin) {
   if (l.type == L_CONV || l.type == L_PAIR) return Lin;
@@ -173,6 +178,15 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   // HBM-bound k = 7 single-channel output convs (conv_post 16->1, LastLayer 32->1): the streaming kernel on both paths
   // (measured 0.305 -> 0.148 ms / 0.457 -> 0.265 ms = 3.5-3.8 TB/s).  The 64->4 conv_post of Multiband-HiFi-GAN is FMA-bound
   // there (0.56 ms) and stays on tcgen05 (0.47 ms) when tensor cores are allowed.
+  if (c.out_split) {
+    if (a.out_layout != OUT_PHASE || !c.allow_tc || tc_disabled || !tcl || !tcl->eligible || c.lens) return FV_NOT_APPLICABLE;
+    a.out_layout = OUT_PHASE_SPLIT;
+    a.out_slope = c.out_slope;
+    int rc = launch_conv_tc2(a, *tcl, st);
+    if (rc < 0) return fail(FV_ECUDA, "tcgen05 conv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == 0 && used_tc) *used_tc = 1;
+    return rc == 0 ? FV_OK : FV_NOT_APPLICABLE;
+  }
   if (narrow7_env && conv_narrow7_ok(a) && (a.N <= 2 || !(c.allow_tc && !tc_disabled && tcl && tcl->eligible))) {
     FV_CUDA(launch_conv_narrow7(a, st));
     return FV_OK;
@@ -242,6 +256,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   const bool mrf_red = tc_ok && mrf_red_env;
   const bool pair_ok = !fuse_disabled_env;   // ResidualStack: fuse the two 1x1 convs (both kernels support two inputs)
   const int Be = eff_batch(m, B, flags);
+  const float mslope = m.mel_slope();
   const size_t each = max_act_floats(m, Be, T);
   const size_t mel_ext_floats = (Be != B) ? ((size_t)Be * c.in_channels * T + 63) / 64 * 64 : 0;
   const size_t need = (6 * each + mel_ext_floats + (lens_host ? lens_floats(Be) : 0)) * sizeof(float);
@@ -295,9 +310,20 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     cudaEventRecord(r.e0, st);
     int rc = run_layer(m.layers[li], wd(li), bias(li), tcl(li), lc, st, &r.used_tc);
     cudaEventRecord(r.e1, st);
+    if (rc == FV_NOT_APPLICABLE) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); return rc; }
     prof->recs.push_back(r);
     return rc;
   };
+  auto pack_split = [&](const float* src, float* dst, int nb, int C, long long Ls, float slope) -> int {
+    dim3 grid((unsigned)std::min<long long>((Ls + 255) / 256, 64), (unsigned)(C / 8), (unsigned)nb);
+    pack_split_kernel<<<grid, 256, 0, st>>>(src, reinterpret_cast<uint4*>(dst), C, (int)Ls, slope);
+    g_launches++;
+    FV_CUDA(cudaGetLastError());
+    return FV_OK;
+  };
+  // Split (TMA-native) activation path of a HiFi-family stage: every ResBlock1 unit of the stage runs as a fused unit whose
+  // input is fetched by TMA from a pre-activated fp16 hi / lo copy.  FV_SPLIT=0 turns it off (A/B and debugging).
+  static const bool split_env = getenv("FV_SPLIT") == nullptr || atoi(getenv("FV_SPLIT")) != 0;
 
   const float* x_in = mel;
   if (Be != B) {  // Basis forward(): append the all-zero utterance (basis_melgan.py:148-151)
@@ -338,11 +364,31 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       const int nb = (int)std::min<long long>(mb, Be - b0);
       const float* x_in_mb = cur + (long long)b0 * in_per_utt;
       float* s_out = other + (long long)b0 * out_per_utt;   // this micro-batch's slice of the stage output
+      // split path: all units of the stage are fused ResBlock1 units that the planner accepts in split mode
+      bool split_stage = m.is_hifi() && tc_ok && fuse_ok && split_env && !lens_dev && tc3_split_available() &&
+                         !sg.branches.empty() && Lout < (1LL << 30);
+      for (size_t j = 0; split_stage && j < sg.branches.size(); ++j)
+        for (const ResUnit& ru : sg.branches[j].units) {
+          Tc3Args probe{};
+          const Layer& la = m.layers[ru.c1];
+          const TcLayer *t1 = tcl(ru.c1), *t2 = ru.c2 >= 0 ? tcl(ru.c2) : nullptr;
+          if (ru.c2 < 0 || !t1 || !t2 || !t1->eligible || !t2->eligible || t1->n_tiles != 1 || t2->n_tiles != 1 ||
+              !tc3_plan(nb, la.Cin, (int)Lout, la.K, la.dil, probe, true)) { split_stage = false; break; }
+        }
       {  // LeakyReLU + ConvTranspose1d
         LayerCall lc;
         lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L; lc.lens = lens_at((int)s - 1, b0);
-        lc.pre_slope = m.is_hifi() ? 0.1f : 0.2f;  // LRELU_SLOPE modules.py:9 / negative_slope 0.2 melgan.py:30
-        if ((rc = call(sg.up, lc))) return rc;
+        lc.pre_slope = m.is_hifi() ? 0.1f : mslope;  // LRELU_SLOPE modules.py:9 / negative_slope melgan.py:30
+        if (split_stage) {   // the upsample layer's epilogue writes lrelu(y) pre-split for the three branches' first convs
+          LayerCall ls = lc;
+          ls.out_split = true; ls.out_slope = 0.1f;
+          rc = call(sg.up, ls);
+          if (rc == FV_NOT_APPLICABLE) {   // not on the tensor-core kernel: fp32 output, then one packing pass
+            lc.y = bufH;
+            if ((rc = call(sg.up, lc))) return rc;
+            if ((rc = pack_split(bufH, bufY, nb, sg.Cout, Lout, 0.1f))) return rc;
+          } else if (rc) return rc;
+        } else if ((rc = call(sg.up, lc))) return rc;
       }
       const int* sl = lens_at((int)s, b0);   // lengths of this stage's tensors
       if (m.is_hifi()) {
@@ -372,8 +418,9 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
                     cudaEventRecord(r.e0, st);
                   }
+                  const int io = !split_stage ? IO_F32 : (last ? IO_SPLIT_F32 : IO_SPLIT_SPLIT);
                   const int frc = launch_fused_unit(bc, dst, bias(br.units[u].c1), bias(br.units[u].c2), *t1, *t2, nb,
-                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st, sl);
+                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st, sl, io);
                   if (prof) {
                     if (frc == 0) { cudaEventRecord(r.e1, st); prof->recs.push_back(r); }
                     else { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -382,6 +429,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                   if (frc == 0) { bc = dst; continue; }
                 }
               }
+              if (split_stage) return fail(FV_ESTATE, "split-path fused unit was not applicable after planning");
               LayerCall l1;
               l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f; l1.lens = sl;
               if ((rc = call(br.units[u].c1, l1))) return rc;
@@ -408,11 +456,11 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
           const Stack& sk = sg.stacks[k];
           float* dst = (k == ns - 1) ? s_out : (k % 2 ? bufY : bufU1);
           LayerCall l1;
-          l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.2f; l1.pad_mode = PAD_REFLECT; l1.lens = sl;
+          l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = mslope; l1.pad_mode = PAD_REFLECT; l1.lens = sl;
           if ((rc = call(sk.dil_conv, l1))) return rc;
           if (pair_ok && sk.pair >= 0) {   // stack.4(lrelu(h)) + skip_layer(c) as one two-input 1x1 GEMM-conv
             LayerCall lp;
-            lp.x = bufH; lp.pre_slope = 0.2f; lp.x2 = sc_in; lp.pre_slope2 = -1.f;
+            lp.x = bufH; lp.pre_slope = mslope; lp.x2 = sc_in; lp.pre_slope2 = -1.f;
             lp.y = dst; lp.B = nb; lp.Lin = Lout; lp.lens = sl;
             if ((rc = call(sk.pair, lp))) return rc;
           } else {
@@ -420,7 +468,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
             ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout; ls.lens = sl;
             if ((rc = call(sk.skip, ls))) return rc;
             LayerCall l2;
-            l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.2f; l2.lens = sl;
+            l2.x = bufH; l2.y = dst; l2.res = bufU0; l2.B = nb; l2.Lin = Lout; l2.pre_slope = mslope; l2.lens = sl;
             if ((rc = call(sk.conv1x1, l2))) return rc;
           }
           sc_in = dst;
@@ -444,7 +492,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     }
   } else if (c.kind == FV_MELGAN) {  // LastLayer (modules.py:85-89) + Tanh (melgan.py:109-110)
     LayerCall lc;
-    lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = 0.2f; lc.pad_mode = PAD_REFLECT;
+    lc.x = cur; lc.y = out; lc.B = Be; lc.Lin = L; lc.pre_slope = mslope; lc.pad_mode = PAD_REFLECT;
     lc.lens = lens_at((int)m.stages.size() - 1, 0);
     lc.post_tanh = c.use_final_activation ? 1 : 0;
     if ((rc = call(m.post, lc))) return rc;
@@ -476,7 +524,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       if (out2) {
         const int C = bl.Cin;
         dim3 g2((unsigned)((L + 31) / 32), (C + 31) / 32, B), b2(32, 8);
-        relu_transpose_sub_kernel<<<g2, b2, 0, st>>>(cur, cur + (long long)B * C * L, out2, C, L);
+        relu_transpose_sub_kernel<<<g2, b2, 0, st>>>(cur, cur + (long long)B * C * L, out2, C, L, c.use_final_activation ? 1 : 0);
         g_launches++;
         FV_CUDA(cudaGetLastError());
       }
@@ -712,10 +760,19 @@ int fv_resblock1(const float* x, const float* const* w1, const float* const* b1,
   float* hbuf = scratch;                          // [B,C,L]
   float* pp[2] = {scratch + (size_t)B * C * L, y};  // ping-pong so the last unit lands in y
   const float* cur = x;
+  if (use_tc == 3) {   // split (TMA-native) chain: pack x once, units hand the split format to each other, the last writes fp32
+    if (!tc3_split_available() || C % 8) return fail(FV_EINVAL, "fv_resblock1: split path unavailable");
+    dim3 grid((unsigned)std::min((L + 255) / 256, 64), (unsigned)(C / 8), (unsigned)B);
+    pack_split_kernel<<<grid, 256, 0, st>>>(x, reinterpret_cast<uint4*>(hbuf), C, L, 0.1f);
+    g_launches++;
+    FV_CUDA(cudaGetLastError());
+    cur = hbuf;
+  }
   for (int u = 0; u < num_dilations; ++u) {
     float* dst = pp[(num_dilations - 1 - u) % 2 ? 0 : 1];
     Layer l1 = make_conv_layer(C, C, K, dilations[u]);
-    if (use_tc == 2) {  // fused-unit kernel (conv1 -> lrelu -> conv2 -> +x in one launch)
+    if (use_tc >= 2) {  // fused-unit kernel (conv1 -> lrelu -> conv2 -> +x in one launch)
+      const int io = use_tc == 3 ? (u == num_dilations - 1 ? IO_SPLIT_F32 : IO_SPLIT_SPLIT) : IO_F32;
       Layer l2f = make_conv_layer(C, C, K, 1);
       TempW t1, t2;
       int rc = t1.make(l1, w1[u], st);
@@ -734,12 +791,13 @@ int fv_resblock1(const float* x, const float* const* w1, const float* const* b1,
       int frc = 1;
       if (tcw.build(two, both, st) == 0 && tcw.layer(0) && tcw.layer(1))
         frc = launch_fused_unit(cur, dst, b1 ? b1[u] : nullptr, b2 ? b2[u] : nullptr, *tcw.layer(0), *tcw.layer(1), B, C,
-                                L, K, dilations[u], 0.1f, ACC_STORE, 1.f, st);
+                                L, K, dilations[u], 0.1f, ACC_STORE, 1.f, st, nullptr, io);
       cudaError_t se = cudaStreamSynchronize(st);
       cudaFree(both);
       tcw.release();
       if (frc < 0 || se != cudaSuccess) return fail(FV_ECUDA, "fused unit failed: %s", cudaGetErrorString(se));
       if (frc == 0) { cur = dst; continue; }
+      if (use_tc == 3) return fail(FV_EINVAL, "fv_resblock1: shape not handled by the split-path fused unit");
     }
     LayerCall c1;
     c1.x = cur; c1.y = hbuf; c1.B = B; c1.Lin = L; c1.pre_slope = 0.1f;
@@ -776,12 +834,29 @@ int fv_residual_stack(const float* c, const float* w_dil, const float* b_dil, co
   return conv_raw(l1, w_1x1, b_1x1, c2, use_tc, st);
 }
 
+int fv_basis_signal(fv_handle* h, const float* weight_bcl, int B, int frames, float* out, int use_tc, void* stream) {
+  if (!h || !weight_bcl || !out || B <= 0 || frames <= 0) return fail(FV_EINVAL, "fv_basis_signal: bad argument");
+  if (!h->bound) return fail(FV_ESTATE, "fv_basis_signal before fv_bind_weights");
+  const Model& m = h->model;
+  if (m.basis < 0) return fail(FV_EINVAL, "fv_basis_signal: not a Basis-MelGAN handle");
+  LayerCall lc;
+  lc.x = weight_bcl; lc.y = out; lc.B = B; lc.Lin = frames; lc.pre_slope = -1.f;   // BasisSignalLayer has no activation
+  lc.allow_tc = use_tc != 0;
+  return run_layer(m.layers[m.basis], h->derived + m.layers[m.basis].wd_offset, nullptr, h->tc.layer(m.basis), lc,
+                   (cudaStream_t)stream);
+}
+
 int fv_overlap_add(const float* frames, int B, int num_frames, int frame_length, int frame_step, float* out,
                    void* stream) {
   if (!frames || !out || B <= 0 || num_frames <= 0) return fail(FV_EINVAL, "fv_overlap_add: bad argument");
-  if (frame_length != 2 * frame_step) return fail(FV_EINVAL, "fv_overlap_add: only frame_length == 2*frame_step");
-  dim3 grid(grid_for((long long)(num_frames + 1) * frame_step), B);
-  overlap_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, out, num_frames, frame_step);
+  if (frame_length <= 0 || frame_step <= 0) return fail(FV_EINVAL, "fv_overlap_add: frame_length / frame_step must be > 0");
+  if (frame_length == 2 * frame_step) {   // the Basis-MelGAN shape (L = 30, hop = 15): two addends per sample
+    dim3 grid(grid_for((long long)(num_frames + 1) * frame_step), B);
+    overlap_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, out, num_frames, frame_step);
+  } else {                                // any other ratio (the reference's gcd sub-frame path, modules.py:57-72)
+    dim3 grid(grid_for((long long)(num_frames - 1) * frame_step + frame_length), B);
+    overlap_add_general_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frames, out, num_frames, frame_length, frame_step);
+  }
   g_launches++;
   FV_CUDA(cudaGetLastError());
   return FV_OK;

@@ -22,7 +22,9 @@ __host__ __device__ inline bool acc_reads_y(int m) { return m == ACC_ADD || m ==
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
-enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2 };
+// OUT_PHASE_SPLIT (tensor-core kernel only): the polyphase ConvTranspose output, LeakyReLU(out_slope)-activated and split
+// into fp16 hi / lo in the blocked "split" activation format the fused ResBlock units fetch by TMA (fv_tma.cuh).
+enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2, OUT_PHASE_SPLIT = 3 };
 
 struct ConvArgs {
   const float* x;     // [B, Cin, Lin]
@@ -40,6 +42,7 @@ struct ConvArgs {
   int bias_mod;
   // OUT_PHASE (ConvTranspose1d): n = r*ph_cout + co ; t = pos*ph_stride + r - ph_pad in [0, ph_lout)
   int ph_stride, ph_pad, ph_cout, ph_lout;
+  float out_slope;               // OUT_PHASE_SPLIT: LeakyReLU slope baked into the split copy (the consumers' pre-activation)
   long long x_bs, y_bs, res_bs;  // batch strides in floats
   // two-input form (L_PAIR): input channels >= cin_split come from x2 (own pre-activation); 0 = single input
   const float* x2;
@@ -767,6 +770,23 @@ __global__ void overlap_add_kernel(const float* __restrict__ f, float* __restric
   }
 }
 
+// General overlap_and_add (modules.py:34-73, any frame_length / frame_step): out[i] = sum over the frames n that cover
+// sample i of f[n, i - n*step], added in increasing n — the order index_add_ visits the gcd sub-frames on the CPU.
+__global__ void overlap_add_general_kernel(const float* __restrict__ f, float* __restrict__ out, int frames, int flen,
+                                           int step) {
+  const int b = blockIdx.y;
+  const long long n_out = (long long)(frames - 1) * step + flen;
+  const float* fb = f + (long long)b * frames * flen;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out; i += (long long)gridDim.x * blockDim.x) {
+    long long n_hi = i / step;
+    if (n_hi > frames - 1) n_hi = frames - 1;
+    long long n_lo = i - flen + 1 <= 0 ? 0 : (i - flen + 1 + step - 1) / step;
+    float v = 0.f;
+    for (long long n = n_lo; n <= n_hi; ++n) v += fb[n * flen + (i - n * step)];
+    out[(long long)b * n_out + i] = v;
+  }
+}
+
 // Basis forward(): est[b, i] = full[b, i] - full[zero, i], i < Ltrunc (full rows have Lfull samples)
 __global__ void sub_broadcast_kernel(const float* __restrict__ full, const float* __restrict__ zero, float* __restrict__ out,
                                      long long Lfull, long long Ltrunc) {
@@ -778,9 +798,35 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, float* __restric
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
+// fp32 [B, C, L] -> "split" activation format (fv_tma.cuh): LeakyReLU(slope) applied, value = hi + lo with hi = the fp32
+// value truncated to 11 significant bits (exactly an fp16), lo = fp16(value - hi); uint4 out[B][2][C/8][L] (8 halfs each).
+// Same arithmetic as the in-kernel split of fv_tc.cuh (split_f16x2) so that both producers of the format agree bit for bit.
+__global__ void pack_split_kernel(const float* __restrict__ x, uint4* __restrict__ out, int C, int L, float slope) {
+  const int nkc = C >> 3;
+  const int b = blockIdx.z, kc = blockIdx.y;
+  const float* xb = x + ((long long)b * C + kc * 8) * L;
+  uint4* oh = out + ((long long)(b * 2) * nkc + kc) * L;
+  uint4* ol = out + ((long long)(b * 2 + 1) * nkc + kc) * L;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const float a0 = xb[(long long)c * L + t], a1 = xb[(long long)(c + 1) * L + t];
+      const float v0 = fmaxf(a0, a0 * slope), v1 = fmaxf(a1, a1 * slope);
+      const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
+      const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+      const float l0 = v0 - h0, l1 = v1 - h1;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hp[c >> 1]) : "f"(h1), "f"(h0));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lp[c >> 1]) : "f"(l1), "f"(l0));
+    }
+    oh[t] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    ol[t] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+}
 // weight[b, l, c] = relu(x[b, c, l]) - relu(x0[c, l])   (basis_melgan.py:154-160)
+// relu = 0 (use_final_nonlinear_activation=False, basis_melgan.py:120-121): the raw predictor output, no ReLU
 __global__ void relu_transpose_sub_kernel(const float* __restrict__ x, const float* __restrict__ x0, float* __restrict__ out,
-                                          int C, long long L) {
+                                          int C, long long L, int relu) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long l0 = (long long)blockIdx.x * 32;
@@ -792,7 +838,7 @@ __global__ void relu_transpose_sub_kernel(const float* __restrict__ x, const flo
     float v = 0.f;
     if (c < C && l < L) {
       const float a = xb[(long long)c * L + l], z = x0 ? x0[(long long)c * L + l] : 0.f;
-      v = fmaxf(a, 0.f) - (x0 ? fmaxf(z, 0.f) : 0.f);
+      v = relu ? fmaxf(a, 0.f) - (x0 ? fmaxf(z, 0.f) : 0.f) : a - z;
     }
     tile[r][threadIdx.x] = v;
   }

@@ -84,6 +84,8 @@ struct Model {
   std::string err;
 
   bool is_hifi() const { return cfg.kind == FV_HIFIGAN || cfg.kind == FV_MB_HIFIGAN; }
+  // LeakyReLU slope of the MelGAN family (nonlinear_activation_params["negative_slope"], melgan.py:30; default 0.2)
+  float mel_slope() const { return cfg.negative_slope_set ? cfg.negative_slope : 0.2f; }
 
   int add_param(const std::string& name, std::initializer_list<int64_t> shape) {
     Param p;
@@ -173,6 +175,8 @@ struct Model {
       if (!c.upsample_layer && c.upsample_kernel_sizes[i] < c.upsample_rates[i]) return fail("upsample kernel < rate unsupported");
     }
     if (c.pre_kernel_size <= 0 || c.pre_kernel_size % 2 == 0) return fail("Not support even number kernel size.");
+    if (c.negative_slope_set && !(c.negative_slope >= 0.f && c.negative_slope <= 1.f))
+      return fail("negative_slope must lie in [0, 1]");
     if (c.use_causal_conv && is_hifi()) return fail("use_causal_conv is a MelGAN-family switch");
     if (c.lastlinear && c.kind != FV_BASIS_MELGAN) return fail("lastlinear is a BasisMelGANGenerator option (basis_melgan.py:38)");
     if (c.upsample_layer && c.kind == FV_MELGAN) return fail("transposedconv=False is not a MelGANGenerator option (melgan.py:20-36)");
@@ -236,7 +240,7 @@ struct Model {
         return fail("Not support even number kernel size.");
       int idx = 1;
       snprintf(buf, sizeof buf, "melgan.%d", idx);
-      pre = add_conv(buf, c.in_channels, c.channels[0], c.pre_kernel_size, 1, true);
+      pre = add_conv(buf, c.in_channels, c.channels[0], c.pre_kernel_size, 1, bias);
       idx = 2;
       for (int i = 0; i < c.num_upsamples; ++i) {
         Stage st;
@@ -244,10 +248,10 @@ struct Model {
         snprintf(buf, sizeof buf, "melgan.%d", idx + 1);
         if (c.upsample_layer)   // basis_melgan.py:82-88: UpsampleLayer(.., kernel_size=2*scale+1, stride=1, padding=scale)
           st.up = add_upconv(buf, c.channels[i], c.channels[i + 1], 2 * c.upsample_rates[i] + 1, c.upsample_rates[i],
-                             c.upsample_rates[i], true);
+                             c.upsample_rates[i], bias);
         else
           st.up = add_convt(buf, c.channels[i], c.channels[i + 1], c.upsample_kernel_sizes[i],
-                            c.upsample_rates[i], true);
+                            c.upsample_rates[i], bias);
         idx += 2;
         int dil = 1;
         for (int j = 0; j < c.stacks; ++j) {
@@ -256,12 +260,12 @@ struct Model {
           // non-causal: stack = [act, pad, conv, act, conv1x1] -> stack.2 / stack.4;  causal: [act, CausalConv1d, act,
           // conv1x1] -> stack.1.conv / stack.3 (modules.py:345-361)
           snprintf(buf, sizeof buf, c.use_causal_conv ? "melgan.%d.stack.1.conv" : "melgan.%d.stack.2", idx);
-          sk.dil_conv = add_conv(buf, st.Cout, st.Cout, c.stack_kernel_size, dil, true);
+          sk.dil_conv = add_conv(buf, st.Cout, st.Cout, c.stack_kernel_size, dil, bias);
           layers[sk.dil_conv].causal = c.use_causal_conv != 0;
           snprintf(buf, sizeof buf, c.use_causal_conv ? "melgan.%d.stack.3" : "melgan.%d.stack.4", idx);
-          sk.conv1x1 = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
+          sk.conv1x1 = add_conv(buf, st.Cout, st.Cout, 1, 1, bias);
           snprintf(buf, sizeof buf, "melgan.%d.skip_layer", idx);
-          sk.skip = add_conv(buf, st.Cout, st.Cout, 1, 1, true);
+          sk.skip = add_conv(buf, st.Cout, st.Cout, 1, 1, bias);
           {  // virtual fused layer over the two 1x1 convs (no parameters of its own)
             Layer pl;
             pl.type = L_PAIR;
@@ -283,12 +287,13 @@ struct Model {
       if (c.kind == FV_MELGAN) {
         if (c.post_kernel_size <= 0 || c.post_kernel_size % 2 == 0) return fail("post kernel must be odd");
         snprintf(buf, sizeof buf, "melgan.%d.conv", idx);
-        post = add_conv(buf, c.channels[c.num_upsamples], c.out_channels, c.post_kernel_size, 1, true);
+        post = add_conv(buf, c.channels[c.num_upsamples], c.out_channels, c.post_kernel_size, 1, bias);
       } else {
         if (c.basis_L <= 0 || c.basis_L % 2) return fail("basis L must be even (hop = L/2)");
         const int Cl = c.channels[c.num_upsamples];
         if (c.lastlinear) {   // basis_melgan.py:117-118, modules.py:116-132
           if (c.out_channels <= 0) return fail("out_channels must be > 0");
+          if (!bias) return fail("lastlinear with bias=False is not supported (the folded BatchNorm needs the bias slot)");
           snprintf(buf, sizeof buf, "melgan.%d.linear_1", idx);
           ll1 = add_conv(buf, Cl, Cl, 1, 1, true);
           snprintf(buf, sizeof buf, "melgan.%d.linear_2", idx);

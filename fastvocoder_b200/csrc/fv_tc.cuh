@@ -22,10 +22,13 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "fv_kernels.cuh"
 #include "fv_model.h"
+#include "fv_tma.cuh"
 
 namespace fv {
 
@@ -210,6 +213,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Two 16-column loads in flight, ONE wait (the epilogues always need the [hi*hi + lo*hi | hi*lo] pair of the dual layout)
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, uint32_t (&r)[16], uint32_t (&q)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr1)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -488,23 +508,36 @@ template <bool DUAL, int MT, bool REUSE = false>
 __device__ __forceinline__ void issue_kblocks(uint64_t ad, uint64_t bd, uint32_t d0, int nkb, uint32_t accum,
                                               uint64_t ks_step16, uint64_t kb16, uint64_t mt_step16, uint32_t d_step,
                                               uint64_t lo_delta16, uint64_t nt16, uint32_t idesc, uint32_t idesc2) {
+  // Issue order: a UMMA that accumulates into the columns the previous one wrote waits for it to drain (~150-250 clk for
+  // these short N <= 128 instructions, profiles/r02_notes.md), so the products of one k-block are issued product-major over
+  // the M tiles (independent accumulators back to back) instead of tile-major.
   for (int q = 0; q < nkb; ++q, ad += ks_step16, bd += kb16) {
+    if (REUSE) {   // single issuer: the hi tile is fetched once for its two products (needs the pair adjacent)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const uint64_t am = ad + (uint64_t)m * mt_step16;
-      const uint32_t d = d0 + (uint32_t)m * d_step;
-      if (DUAL) {
-        umma_f16_elect(d, am, bd, idesc2, accum);               // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
-        umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);      // lo*hi -> cols [0,NT)
-      } else if (REUSE) {   // single issuer: the hi tile is fetched once for its two products
+      for (int m = 0; m < MT; ++m) {
+        const uint64_t am = ad + (uint64_t)m * mt_step16;
+        const uint32_t d = d0 + (uint32_t)m * d_step;
         umma_f16_elect_fill(d, am, bd, idesc, accum);
         umma_f16_elect_lastuse(d, am, bd + nt16, idesc, 1u);
         umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);
-      } else {
-        umma_f16_elect(d, am, bd, idesc, accum);
-        umma_f16_elect(d, am, bd + nt16, idesc, 1u);            // + NT*16 bytes: the lo half of the block
-        umma_f16_elect(d, am + lo_delta16, bd, idesc, 1u);
       }
+    } else if (DUAL) {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)   // [hi*hi | hi*lo] -> cols [0,NT) | [NT,2NT)
+        umma_f16_elect(d0 + (uint32_t)m * d_step, ad + (uint64_t)m * mt_step16, bd, idesc2, accum);
+#pragma unroll
+      for (int m = 0; m < MT; ++m)   // lo*hi -> cols [0,NT)
+        umma_f16_elect(d0 + (uint32_t)m * d_step, ad + (uint64_t)m * mt_step16 + lo_delta16, bd, idesc, 1u);
+    } else {
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        umma_f16_elect(d0 + (uint32_t)m * d_step, ad + (uint64_t)m * mt_step16, bd, idesc, accum);
+#pragma unroll
+      for (int m = 0; m < MT; ++m)   // + NT*16 bytes: the lo half of the block
+        umma_f16_elect(d0 + (uint32_t)m * d_step, ad + (uint64_t)m * mt_step16, bd + nt16, idesc, 1u);
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+        umma_f16_elect(d0 + (uint32_t)m * d_step, ad + (uint64_t)m * mt_step16 + lo_delta16, bd, idesc, 1u);
     }
     accum = 1u;
   }
@@ -543,11 +576,12 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
   const int nchunks = p.NT >> 4;
   for (int c = 0; c < nchunks; ++c) {
     const int nbase = nt * p.NT + c * 16;
+    constexpr bool PHASED = (LAYOUT == OUT_PHASE || LAYOUT == OUT_PHASE_SPLIT);
     int r = 0, co0 = nbase;
-    if (LAYOUT == OUT_PHASE) { r = nbase / a.ph_cout; co0 = nbase - r * a.ph_cout; }
+    if (PHASED) { r = nbase / a.ph_cout; co0 = nbase - r * a.ph_cout; }
     float bias[16];
-    if (a.bias && (LAYOUT == OUT_PHASE || nbase + 16 <= a.N)) {
-      const float4* bp = reinterpret_cast<const float4*>(a.bias + (LAYOUT == OUT_PHASE ? co0 : nbase));
+    if (a.bias && (PHASED || nbase + 16 <= a.N)) {
+      const float4* bp = reinterpret_cast<const float4*>(a.bias + (PHASED ? co0 : nbase));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 v = __ldg(bp + i);
@@ -583,8 +617,25 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         o0 = co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
       if (!ok) continue;
+      if (LAYOUT == OUT_PHASE_SPLIT) {
+        // split copy for the TMA-fed fused units: lrelu(out_slope) -> fp16 hi / lo -> rows of 16 B in the blocked planes
+        // uint4 [2 (hi, lo)][Cout/8][Lout]; a 16-column chunk covers planes co0/8 and co0/8 + 1 of both halves
+        uint32_t hp[8], lp[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          split_f16x2(lrelu01(__uint_as_float(rr[i]) + bias[i], a.out_slope),
+                      lrelu01(__uint_as_float(rr[i + 1]) + bias[i + 1], a.out_slope), hp[i >> 1], lp[i >> 1]);
+        uint4* yq = opaque_ptr(reinterpret_cast<uint4*>(yb) + ((co0 >> 3) * a.ph_lout + (o0 - co0 * a.ph_lout)));
+        const uint32_t ul = (uint32_t)a.ph_lout, lo_off = (uint32_t)(a.ph_cout >> 3) * ul;
+        yq[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        yq[ul] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        yq[lo_off] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        yq[lo_off + ul] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+        if (DBG) wa.w[4] += clock64() - tdbg;
+        continue;
+      }
       float* py = opaque_ptr(yb + o0);
-      if (LAYOUT != OUT_PHASE && nbase + 16 > a.N) {   // zero-padded tail columns (Basis 15 of 16, conv_post 1 / 4 of 16)
+      if (!PHASED && nbase + 16 > a.N) {   // zero-padded tail columns (Basis 15 of 16, conv_post 1 / 4 of 16)
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (nbase + i < a.N) {
@@ -1020,6 +1071,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) tc2_epilogue_tile_add<DBG>(p, acc, q, lane, b, t0, nt, wa);
       else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa);
       else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa);
+      else if (a.out_layout == OUT_PHASE_SPLIT) tc2_epilogue_tile<OUT_PHASE_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa);
       else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa);
       tc_fence_before();
       __syncwarp();
@@ -1054,7 +1106,9 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   if ((a.res != nullptr || a.acc_mode != ACC_STORE) && (a.out_layout != OUT_BCL || a.post_tanh)) return false;
   {  // the kernels index inside one utterance's input / output plane with 32-bit element offsets
     const long long lim = 0x7fffffffLL - 65536;
-    const long long out_plane = a.out_layout == OUT_PHASE ? (long long)a.ph_cout * a.ph_lout : (long long)L.n_pad * a.Lpos;
+    const long long out_plane = (a.out_layout == OUT_PHASE || a.out_layout == OUT_PHASE_SPLIT) ? (long long)a.ph_cout * a.ph_lout
+                                                                                              : (long long)L.n_pad * a.Lpos;
+    if (a.out_layout == OUT_PHASE_SPLIT && (a.ph_cout % 16 || !(a.out_slope >= 0.f && a.out_slope <= 1.f) || a.post_tanh)) return false;
     if ((long long)a.Cin * a.Lin >= lim || out_plane >= lim) return false;
   }
   struct Cand { int mt, a_st, res, w_st, ck, kbps, dual; double score; };
@@ -1323,6 +1377,11 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
 // outputs (conv2's halo is recomputed), x rows = 128m + (K-1)*dil.
 // =================================================================================================
 constexpr int TC3_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 8) * 32;   // + 4 epiA warps + 4 epiB warps
+// Split (TMA-fed) units have no loader warps.  Resident-weight plans: warps 0-3 / 4-7 become a SECOND epiA / epiB group (a
+// TMEM lane quarter is served by two warps that take alternate (chunk, M tile) iterations) and warp 11 — the weight
+// producer, idle once the images are resident; at most 3 issuers then — is the TMA producer.  Streamed-weight plans (warp
+// 11 feeds the ring; issuer-bound anyway): one epilogue group, warp 0 is the TMA producer.  (A 21st warp would put six
+// warps on one SM sub-partition and cap the kernel at 80 registers.)
 
 struct Tc3Args {
   const float* x;      // unit input [B, C, L] (also the residual)
@@ -1345,6 +1404,15 @@ struct Tc3Args {
   uint32_t idesc, idesc2;
   int ld_per, ld_rounds;   // flattened loader (fill_stage_flat); 0 = legacy pair loop
   int pdl;                 // launched with programmatic stream serialization
+  // Split ("TMA-native") activation I/O (template parameter IO of the kernel, fv_tma.cuh): the unit input arrives
+  // pre-activated and pre-split as fp16 hi / lo planes xs[B][2][C/8][L] (uint4 rows) and is fetched by TMA straight into
+  // the A1 stage (no loader warps, OOB rows zero-filled = the conv's zero padding); the residual is rebuilt from the
+  // same planes (x = unlrelu(hi + lo)); IO_SPLIT_SPLIT units write their output in the same format for the next unit.
+  const void* xs;
+  void* ys;
+  float inv_slope;         // 1 / slope (slope > 0): undoes the LeakyReLU baked into the split copy
+  int x_rows_alloc;        // row stride of the A1 planes (x_rows rounded up to 8 in split mode: 128-B aligned TMA boxes)
+  int epi_groups;          // split mode: 1 or 2 warps per TMEM lane quarter in each of epiA / epiB
   // Streamed weights (the two images do not fit next to the tiles: C = 64, k = 7 / 11): warp 11 feeds a ring of
   // `w_stages` slots, one slot = one tap (ksteps k-blocks = stage_bytes), in the order the issuers consume them
   // (conv1 of tile 0, then per tile conv2(i), conv1(i+1)).  Resident mode: w_resident = 1.
@@ -1374,12 +1442,29 @@ __device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_
   }
 }
 
-template <bool DBG>
-__global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p) {
+enum { IO_F32 = 0, IO_SPLIT_SPLIT = 1, IO_SPLIT_F32 = 2 };
+
+// hi / lo rows (8 channels each) of the split copy -> the un-activated fp32 values: v = hi + lo (exact in fp32),
+// x = min(v, v / slope) undoes LeakyReLU for 0 < slope <= 1.
+__device__ __forceinline__ void unsplit8(const uint4& h, const uint4& l, float inv_slope, float* out) {
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ll[j]));
+    const float v0 = fh.x + fl.x, v1 = fh.y + fl.y;
+    out[2 * j] = fminf(v0, v0 * inv_slope);
+    out[2 * j + 1] = fminf(v1, v1 * inv_slope);
+  }
+}
+
+template <bool DBG, int IO>
+__global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p, const __grid_constant__ CUtensorMap tm_main,
+                                                                        const __grid_constant__ CUtensorMap tm_tail) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
   const int C = p.C, NT = p.C;
-  const uint32_t a1_bytes = (uint32_t)p.x_rows * C * 2;        // hi or lo of one A1 stage
+  const uint32_t a1_bytes = (uint32_t)p.x_rows_alloc * C * 2;  // hi or lo of one A1 stage
   const uint32_t a2_bytes = (uint32_t)p.h_rows_alloc * C * 2;  // hi or lo of A2
   const int kblock_bytes = NT * 64;
   const uint32_t w_bytes = (uint32_t)p.kblocks * kblock_bytes;
@@ -1397,20 +1482,25 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
+  const int epi_groups = (IO != IO_F32 && p.epi_groups == 2) ? 2 : 1;
+  // epilogue roles: group 0 = warps 12-15 (epiA) / 16-19 (epiB); split mode with two groups: + warps 0-3 / 4-7
+  const bool is_epiA = (warp >= 12 && warp < 16) || (epi_groups == 2 && warp < 4);
+  const bool is_epiB = (warp >= 16 && warp < 20) || (epi_groups == 2 && warp >= 4 && warp < 8);
+  const int epi_grp = warp < TC2_LOADER_WARPS ? 1 : 0;
   if (p.pdl) pdl_launch_dependents();
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(0 + s), TC2_LOADER_WARPS);
+      mbar_init(BAR(0 + s), IO == IO_F32 ? TC2_LOADER_WARPS : 1);   // split mode: one expect_tx arrive + the TMA bytes
       mbar_init(BAR(2 + s), p.n_issuers);
       mbar_init(BAR(4 + s), p.n_issuers);
-      mbar_init(BAR(6 + s), 4);
+      mbar_init(BAR(6 + s), 4 * epi_groups);
     }
-    mbar_init(BAR(8), 4);
-    mbar_init(BAR(9), p.pp ? 4 : p.n_issuers);   // pp: h_full of the odd buffer; else a2_empty
+    mbar_init(BAR(8), 4 * epi_groups);
+    mbar_init(BAR(9), p.pp ? 4 * epi_groups : p.n_issuers);   // pp: h_full of the odd buffer; else a2_empty
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(10 + s), p.n_issuers);
-      mbar_init(BAR(12 + s), 4);
+      mbar_init(BAR(12 + s), 4 * epi_groups);
     }
     mbar_init(BAR(14), 1);
     for (int s = 0; s < 4; ++s) {
@@ -1428,7 +1518,40 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   // single-buffered A1: conv2(i) is issued before conv1(i+1) so that it never waits behind the load of the next tile
   const bool conv2_first = p.a1_stages == 1;
 
-  if (warp < TC2_LOADER_WARPS) {
+  // ------------------------------------------------------------------ TMA producer loop (one warp, see TC3 role notes)
+  auto tma_producer = [&]() {
+      const int rows = p.x_rows, nkc = C >> 3;
+      const int nfull = rows / TMA_SPLIT_RB, tail = rows - nfull * TMA_SPLIT_RB;
+      const int nrb = nfull + (tail ? 1 : 0);
+      const int per_half = nkc * nrb, nops = 2 * per_half;
+      const uint32_t tile_bytes = (uint32_t)(2 * nkc * rows * 16);
+      if (lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_tail); }
+      int it = 0;
+      WaitAcc<DBG> wa;
+      wa.begin();
+      if (p.pdl) pdl_wait();
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % p.a1_stages;
+        if (it >= p.a1_stages) wa.wait(0, BAR(2 + s), (uint32_t)((it / p.a1_stages - 1) & 1), 800 + s);
+        const int b = tile / p.tiles_per_batch;
+        const int g0 = (tile - b * p.tiles_per_batch) * p.m_out - p2 - p1;
+        if (lane == 0) mbar_expect_tx(BAR(0 + s), tile_bytes);
+        __syncwarp();
+        const uint32_t a_hi = smem_u32(A1 + (size_t)s * 2 * a1_bytes);
+        for (int i = lane; i < nops; i += 32) {
+          const int half = i >= per_half ? 1 : 0;
+          const int rem = i - half * per_half;
+          const int kc = rem / nrb, rb = rem - kc * nrb;
+          const uint32_t dst = a_hi + (uint32_t)half * a1_bytes + (uint32_t)(kc * p.x_rows_alloc + rb * TMA_SPLIT_RB) * 16u;
+          tma_load_2d(dst, rb < nfull ? &tm_main : &tm_tail, 2 * (g0 + rb * TMA_SPLIT_RB), (b * 2 + half) * nkc + kc, BAR(0 + s));
+        }
+      }
+      wa.end(p.dbg, 0, lane == 0, it);
+  };
+  const int tma_warp = p.w_resident ? TC2_LOADER_WARPS + TC2_ISSUE_WARPS - 1 : 0;
+  if (IO != IO_F32 && !p.w_resident && warp == 0) {
+    tma_producer();
+  } else if (IO == IO_F32 && warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
     const int rows = p.x_rows;
     const int nkc = C >> 3;
@@ -1499,7 +1622,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       }
     }
     wa.end(p.dbg, 0, warp == 0 && lane == 0, it);
-  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
+  } else if (warp >= TC2_LOADER_WARPS && warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weights (once) + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;
     const bool L0 = (lane == 0);
@@ -1513,6 +1636,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
           }
         }
+        __syncwarp();
+        if (IO != IO_F32 && warp == tma_warp) tma_producer();   // split mode: this warp is not an issuer (n_issuers <= 3)
       } else if (wid == TC2_ISSUE_WARPS - 1) {
         // ring producer (n_issuers <= 3 in ring mode): one slot per tap, in the issuers' consumption order
         WaitAcc<DBG> wa;
@@ -1557,7 +1682,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         int gw = 0;                                   // ring mode: taps consumed so far
         const uint32_t b_lbo = (uint32_t)NT * 32;
         const uint64_t b_tmpl = make_kmajor_desc(0, b_lbo, 128);
-        const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows * 16, 128);
+        const uint64_t a1_tmpl = make_kmajor_desc(0, (uint32_t)p.x_rows_alloc * 16, 128);
         const uint64_t a2_tmpl = make_kmajor_desc(0, (uint32_t)p.h_rows_alloc * 16, 128);
         const uint32_t mt_cols = (uint32_t)(2 * NT);
         const uint32_t mt_step16 = 128u * (uint32_t)p.n_issuers;
@@ -1587,10 +1712,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bdj += kb_step16) {
                 uint64_t a = ad;
                 uint32_t d = d0;
-                for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) {
-                  umma_f16_elect(d, a, bdj, idesc2, accum);
-                  umma_f16_elect(d, a + lo_delta, bdj, idesc, 1u);
-                }
+                for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) umma_f16_elect(d, a, bdj, idesc2, accum);
+                a = ad + lo_delta; d = d0;   // product-major: independent accumulators back to back (see issue_kblocks)
+                for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) umma_f16_elect(d, a, bdj, idesc, 1u);
                 accum = 1u;
               }
               umma_commit_elect(BAR(19 + slot));      // the slot may be refilled once these UMMAs have read it
@@ -1608,10 +1732,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bd += kb_step16) {
               uint64_t a = ad;
               uint32_t d = d0;
-              for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) {
-                umma_f16_elect(d, a, bd, idesc2, accum);
-                umma_f16_elect(d, a + lo_delta, bd, idesc, 1u);
-              }
+              for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) umma_f16_elect(d, a, bd, idesc2, accum);
+              a = ad + lo_delta; d = d0;
+              for (int mt = wid; mt < m_tiles; mt += n_iss, a += mt_step16, d += d_step) umma_f16_elect(d, a, bd, idesc, 1u);
               accum = 1u;
             }
           }
@@ -1627,7 +1750,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             wa.wait(2, BAR(6 + as), (uint32_t)((i / p.acc1_stages - 1) & 1), 830 + as);
           }
           tc_fence_after();
-          run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w1s, p.dil,
+          run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows_alloc, a1_bytes >> 4, w1s, p.dil,
                    tmem_base + (uint32_t)(as * p.acc_cols));
           if (!p.pp) umma_commit_elect(BAR(2 + s));   // pp: the buffer stays busy (h in place) until conv2 is done
           umma_commit_elect(BAR(4 + as));
@@ -1637,7 +1760,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           if (p.pp) {   // h sits in the tile's own buffer (row stride x_rows), the accumulators are the drained conv1 set
             wa.wait(3, BAR(8 + bs), (uint32_t)((i / 2) & 1), 840 + bs);
             tc_fence_after();
-            run_conv(a1_tmpl, smem_u32(A1 + (size_t)bs * 2 * a1_bytes), (uint32_t)p.x_rows, a1_bytes >> 4, w2s, 1,
+            run_conv(a1_tmpl, smem_u32(A1 + (size_t)bs * 2 * a1_bytes), (uint32_t)p.x_rows_alloc, a1_bytes >> 4, w2s, 1,
                      tmem_base + (uint32_t)(bs * p.acc_cols));
             umma_commit_elect(BAR(2 + bs));   // buffer free for the loader
             umma_commit_elect(BAR(10 + bs));
@@ -1672,7 +1795,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       }
     }
     __syncwarp();
-  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 4) {
+  } else if (is_epiA) {
     // ------------------------------------------------------------------ epiA warps: acc1 -> A2 (shared memory)
     const int q = warp & 3;
     const int nchunks = NT >> 4;
@@ -1692,7 +1815,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         if (p.pp) {   // in place: conv1 (whose completion acc1_full signals) was the last reader of this buffer's x tile
           A2_hi = A1 + (size_t)as * 2 * a1_bytes;
           A2_lo = A2_hi + a1_bytes;
-          h_rows = (uint32_t)p.x_rows;
+          h_rows = (uint32_t)p.x_rows_alloc;
         } else if (it >= 1) {
           wa.wait(1, BAR(9), (uint32_t)((it - 1) & 1), 870);
         }
@@ -1712,13 +1835,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             for (int i = 0; i < 16; ++i) b1v[i] = 0.f;
           }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
+            if (epi_groups == 2 && ((c * p.m_tiles + mt) & 1) != epi_grp) continue;   // the quarter's other warp takes it
             const int r = mt * 128 + q * 32 + lane;
             const int gpos = t0 - p2 + r;
             const bool inside = gpos >= 0 && gpos < Lb;
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
-            tmem_ld16(tcol, rr);
-            tmem_ld16(tcol + (uint32_t)NT, r2);
+            tmem_ld16x2(tcol, tcol + (uint32_t)NT, rr, r2);
             uint32_t hp[8], lp[8];
             const uint32_t keep = inside ? 0xffffffffu : 0u;   // rows outside the sequence are conv2's zero padding
 #pragma unroll
@@ -1756,8 +1879,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         }
       }
     }
-    wa.end(p.dbg, 4, q == 0 && lane == 0, it);
-  } else {
+    wa.end(p.dbg, 4, q == 0 && lane == 0 && epi_grp == 0, it);
+  } else if (is_epiB) {
     // ------------------------------------------------------------------ epiB warps: acc2 -> global
     const int q = warp & 3;
     const int nchunks = NT >> 4;
@@ -1790,16 +1913,28 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             for (int i = 0; i < 16; ++i) bias[i] = 0.f;
           }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
+            if (epi_groups == 2 && ((c * p.m_tiles + mt) & 1) != epi_grp) continue;
             const int r = mt * 128 + q * 32 + lane;
             const int t = t0 + r;
             const bool ok = r < p.m_out && t < p.L;
             const int o0 = (c * 16) * p.L + t;   // 32-bit offset inside the utterance plane (tc3_plan: C*L < 2^31)
             // the residual does not depend on the accumulators: issue its loads before waiting for the UMMAs
             float xv[16];
-            const float* px = opaque_ptr(xb + (ok ? o0 : 0));
             float* py = opaque_ptr(yb + (ok ? o0 : 0));
+            // split copies: plane kc of half hf at uint4 index (hf * C/8 + kc) * L + t inside the utterance
+            const uint32_t q_h0 = (uint32_t)(2 * c) * uL + (uint32_t)(ok ? t : 0), q_lo = (uint32_t)(C >> 3) * uL;
+            if (IO == IO_F32) {
+              const float* px = opaque_ptr(xb + (ok ? o0 : 0));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(px + (uint32_t)i * uL) : 0.f;
+              for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(px + (uint32_t)i * uL) : 0.f;
+            } else {
+              const uint4* pq = opaque_ptr(reinterpret_cast<const uint4*>(p.xs) + (long long)b * (2 * (C >> 3)) * p.L + q_h0);
+              const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+              const uint4 h0 = ok ? __ldg(pq) : z4, h1 = ok ? __ldg(pq + uL) : z4;
+              const uint4 l0 = ok ? __ldg(pq + q_lo) : z4, l1 = ok ? __ldg(pq + q_lo + uL) : z4;
+              unsplit8(h0, l0, p.inv_slope, xv);
+              unsplit8(h1, l1, p.inv_slope, xv + 8);
+            }
             if (acc_reads_y(p.acc_mode)) {   // running MRF sum: fold it into the prefetched addend (x + xs)
 #pragma unroll
               for (int i = 0; i < 16; ++i) xv[i] += ok ? py[(uint32_t)i * uL] : 0.f;
@@ -1811,8 +1946,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             }
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
-            tmem_ld16(tcol, rr);
-            tmem_ld16(tcol + (uint32_t)NT, r2);
+            tmem_ld16x2(tcol, tcol + (uint32_t)NT, rr, r2);
             if (!ok) continue;
             float v[16];
 #if FV_PACKED_F32
@@ -1834,7 +1968,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               for (int i = 0; i < 16; ++i) v[i] *= inv;
             }
 #endif
-            if (p.acc_mode == ACC_RED_SCALE) {   // y += v / num_kernels without reading y (one thread per element)
+            if (IO == IO_SPLIT_SPLIT) {   // next unit's input: lrelu -> fp16 hi / lo rows of the blocked planes
+              uint32_t hp[8], lp[8];
+#pragma unroll
+              for (int i = 0; i < 16; i += 2)
+                split_f16x2(lrelu01(v[i], p.slope), lrelu01(v[i + 1], p.slope), hp[i >> 1], lp[i >> 1]);
+              uint4* pw = opaque_ptr(reinterpret_cast<uint4*>(p.ys) + (long long)b * (2 * (C >> 3)) * p.L + q_h0);
+              pw[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+              pw[uL] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+              pw[q_lo] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+              pw[q_lo + uL] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+            } else if (p.acc_mode == ACC_RED_SCALE) {   // y += v / num_kernels without reading y (one thread per element)
 #pragma unroll
               for (int i = 0; i < 16; ++i) red_add_f32(py + (uint32_t)i * uL, v[i]);
             } else {
@@ -1843,12 +1987,16 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             }
           }
         }
+        if (!waited) {   // a warp without an iteration in this tile still follows the accumulator hand-shake
+          wa.wait(0, BAR(10 + bs), (uint32_t)((it / p.acc2_stages) & 1), 880 + bs);
+          tc_fence_after();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(12 + bs));
       }
     }
-    wa.end(p.dbg, 5, q == 0 && lane == 0, it);
+    wa.end(p.dbg, 5, q == 0 && lane == 0 && epi_grp == 0, it);
   }
   tc_fence_before();
   __syncthreads();
@@ -1857,15 +2005,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 
 inline size_t tc3_smem_bytes(const Tc3Args& p) {
   const size_t w = p.w_resident ? 2ULL * p.kblocks * p.C * 64 : (size_t)p.w_stages * p.stage_bytes;
-  return (size_t)p.a1_stages * 2 * p.x_rows * p.C * 2 + (p.pp ? 0 : 2ULL * p.h_rows_alloc * p.C * 2) + w + 24 * 8;
+  return (size_t)p.a1_stages * 2 * p.x_rows_alloc * p.C * 2 + (p.pp ? 0 : 2ULL * p.h_rows_alloc * p.C * 2) + w + 24 * 8;
 }
 
 // conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64).
 // Both images resident in shared memory when they fit; otherwise (C = 64, k = 7 / 11) they are streamed through a ring,
 // one tap per slot, and the tile is made as tall as TMEM allows (single accumulator sets) because every tile re-streams
 // all 2*K taps from L2: positions per weight pass is what bounds those units.
-inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p) {
+inline bool tc3_plan(int B, int C, int L, int K, int dil, Tc3Args& p, bool split = false) {
   if (C % 16 || C > 64 || K % 2 == 0) return false;
+  // split (TMA-fed) units: A1 plane stride rounded up to 8 rows so that every TMA box lands 128-byte aligned
+  auto xr = [split](long long rows) { return split ? (rows + 7) / 8 * 8 : rows; };
   if ((long long)C * L >= 0x7fffffffLL - 65536) return false;   // 32-bit offsets inside the utterance plane
   const int ksteps = C / 16, kblocks = K * ksteps;
   const long long BUDGET = 225 * 1024;
@@ -1881,7 +2031,7 @@ retry:
       for (int m = 8; m >= 1; --m) {
         if (force_m > 0 && m != force_m) continue;
         if ((acc1 + 2) * m * 2 * C > 512) continue;
-        const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
+        const long long x_rows = xr(128LL * m + (long long)(K - 1) * dil), h_alloc = 128LL * m + (K - 1);
         const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + 2LL * kblocks * C * 64 + 256;
         if (sm > BUDGET) continue;
         const int m_out = 128 * m - (K - 1);
@@ -1907,7 +2057,7 @@ retry:
     for (int m = 8; m > best_m; --m) {
       if (pp_m_env > 0 && m > pp_m_env) continue;
       if (2 * m * 2 * C > 512) continue;
-      const long long x_rows = 128LL * m + (long long)(K - 1) * dil;
+      const long long x_rows = xr(128LL * m + (long long)(K - 1) * dil);
       const long long sm = 2 * 2 * x_rows * C * 2 + 2LL * kblocks * C * 64 + 256;
       if (sm > BUDGET) continue;
       const int m_out = 128 * m - (K - 1);
@@ -1925,7 +2075,7 @@ retry:
       if (ring_m_env > 0 && m != ring_m_env) continue;
       if (2 * m * 2 * C > 512 || 128 * m - (K - 1) <= 0) continue;
       for (int wst = 4; wst >= 3; --wst) {
-        const long long x_rows = 128LL * m + (long long)(K - 1) * dil;
+        const long long x_rows = xr(128LL * m + (long long)(K - 1) * dil);
         const long long sm = 2 * 2 * x_rows * C * 2 + wst * stage_bytes + 256;
         if (sm > BUDGET) continue;
         best_sc = 1.0; best_m = m; best_a1 = 2; best_acc1 = 2; best_acc2 = 2; best_res = 0; best_wst = wst; best_pp = 1;
@@ -1939,7 +2089,7 @@ retry:
         if (2 * acc * m * 2 * C > 512) continue;
         for (int a1 = 2; a1 >= 1 && best_sc < 0; --a1)
           for (int wst = 4; wst >= 3; --wst) {
-            const long long x_rows = 128LL * m + (long long)(K - 1) * dil, h_alloc = 128LL * m + (K - 1);
+            const long long x_rows = xr(128LL * m + (long long)(K - 1) * dil), h_alloc = 128LL * m + (K - 1);
             const long long sm = a1 * 2 * x_rows * C * 2 + 2 * h_alloc * C * 2 + wst * stage_bytes + 256;
             if (sm > BUDGET || 128 * m - (K - 1) <= 0) continue;
             best_sc = 1.0; best_m = m; best_a1 = a1; best_acc1 = acc; best_acc2 = acc; best_res = 0; best_wst = wst;
@@ -1953,6 +2103,7 @@ retry:
   p.B = B; p.C = C; p.L = L; p.K = K; p.dil = dil;
   p.m_tiles = best_m;
   p.x_rows = 128 * best_m + (K - 1) * dil;
+  p.x_rows_alloc = (int)xr(p.x_rows);
   p.h_rows_alloc = 128 * best_m + (K - 1);
   p.m_out = 128 * best_m - (K - 1);
   p.a1_stages = best_a1;
@@ -1962,7 +2113,8 @@ retry:
   p.pp = best_pp;
   p.w_stages = best_wst;
   p.stage_bytes = (int)stage_bytes;
-  p.n_issuers = std::min(best_m, best_res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);   // ring mode: warp 11 is the producer
+  // ring mode: warp 11 is the weight producer; split mode: warp 11 is the TMA producer once the images are resident
+  p.n_issuers = std::min(best_m, (best_res && !split) ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);
   static const int force_iss = getenv("FV_TC3_ISSUERS") ? atoi(getenv("FV_TC3_ISSUERS")) : 0;   // tuning knob
   if (force_iss > 0) p.n_issuers = std::max(1, std::min(p.n_issuers, force_iss));
   p.acc_cols = best_m * 2 * C;
@@ -1985,33 +2137,64 @@ retry:
   return true;
 }
 
-// returns 0 launched, 1 not applicable, -1 CUDA error
+// Is the split (TMA-native) activation path usable at all on this machine?  (driver exports cuTensorMapEncodeTiled)
+inline bool tc3_split_available() { return tma_encode_fn() != nullptr; }
+
+// returns 0 launched, 1 not applicable, -1 CUDA error.
+// io = IO_F32: x / y are fp32 [B, C, L].  IO_SPLIT_SPLIT / IO_SPLIT_F32: x is a split-format buffer (fv_tma.cuh) and, for
+// IO_SPLIT_SPLIT, so is y (acc_mode must be ACC_STORE); lens (ragged batches) is not supported in split mode.
 inline int launch_fused_unit(const float* x, float* y, const float* b1, const float* b2, const TcLayer& l1,
                              const TcLayer& l2, int B, int C, int L, int K, int dil, float slope, int acc_mode,
-                             float acc_div, cudaStream_t st, const int* lens = nullptr) {
+                             float acc_div, cudaStream_t st, const int* lens = nullptr, int io = IO_F32) {
   if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
   tc_apply_env_once();
   Tc3Args p{};
   if (!(slope >= 0.f && slope <= 1.f)) return 1;   // lrelu01
-  if (!tc3_plan(B, C, L, K, dil, p)) return 1;
+  if (io != IO_F32 && (lens != nullptr || !(slope > 0.f) || !tc3_split_available())) return 1;
+  if (io == IO_SPLIT_SPLIT && acc_mode != ACC_STORE) return 1;
+  if (!tc3_plan(B, C, L, K, dil, p, io != IO_F32)) return 1;
   p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2; p.lens = lens;
+  p.xs = x; p.ys = y;
+  p.inv_slope = slope > 0.f ? 1.0f / slope : 1.0f;
+  static const int epi_env = getenv("FV_TC3_EPI") ? atoi(getenv("FV_TC3_EPI")) : 2;   // epilogue warp groups in split mode
+  p.epi_groups = (io != IO_F32 && epi_env >= 2 && p.w_resident) ? 2 : 1;
   p.w1img = l1.image; p.w2img = l2.image;
   p.slope = slope; p.acc_mode = acc_mode; p.acc_div = acc_div;
+  CUtensorMap tm_main, tm_tail;
+  memset(&tm_main, 0, sizeof tm_main);
+  memset(&tm_tail, 0, sizeof tm_tail);
+  if (io != IO_F32) {
+    const long long planes = (long long)B * 2 * (C / 8);
+    const int tail = p.x_rows % TMA_SPLIT_RB;
+    if (!tma_encode_split(&tm_main, x, L, planes, TMA_SPLIT_RB)) return 1;
+    if (tail) {
+      if (!tma_encode_split(&tm_tail, x, L, planes, tail)) return 1;
+    } else {
+      tm_tail = tm_main;
+    }
+  }
+  static std::mutex mu;
   static bool attr_set[64] = {};
   static int num_sms[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(conv_tc3_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc3_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
-            cudaSuccess)
-      return -1;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
-    num_sms[dev] = prop.multiProcessorCount;
-    attr_set[dev] = true;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_set[dev]) {
+      const int mx = 227 * 1024;
+      if (cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+        return -1;
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+      num_sms[dev] = prop.multiProcessorCount;
+      attr_set[dev] = true;
+    }
   }
   int gx = std::min(num_sms[dev], p.total_tiles);
   cudaLaunchConfig_t cfg{};
@@ -2027,11 +2210,14 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
+  cudaError_t le;
   if (tc_stall_debug()) {
     StallReport rep;
     if (!rep.begin(gx)) return -1;
     p.dbg = rep.dev;
-    conv_tc3_fused_kernel<true><<<gx, TC3_THREADS, tc3_smem_bytes(p), st>>>(p);
+    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_F32>, p, tm_main, tm_tail);
+    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
+    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_F32>, p, tm_main, tm_tail);
     static const char* const roles[8] = {"loader", "producer", "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
     static const char* const slots[8][5] = {{"a1_empty", nullptr, nullptr, nullptr, nullptr},
                                             {"w_empty", nullptr, nullptr, nullptr, nullptr},
@@ -2041,13 +2227,16 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
                                             {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
     char title[256];
     snprintf(title, sizeof title,
-             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d pp=%d issuers=%d "
-             "tiles=%d grid=%d", C, K, dil, L, B, acc_mode, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
+             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d io=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d pp=%d issuers=%d "
+             "tiles=%d grid=%d", C, K, dil, L, B, acc_mode, io, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
              p.w_resident, p.w_stages, p.pp, p.n_issuers, p.total_tiles, gx);
     rep.finish(st, title, roles, slots);
   } else {
-    if (cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false>, p) != cudaSuccess) return -1;
+    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_F32>, p, tm_main, tm_tail);
+    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
+    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_F32>, p, tm_main, tm_tail);
   }
+  if (le != cudaSuccess) return -1;
   g_launches++;
   g_tc_launches++;
   return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -59,6 +59,9 @@ class _NativeGenerator(torch.nn.Module):
         self._bound_key = None
         self._workspace = None
         self.use_tensor_cores = True
+        # inference(): replay a CUDA graph captured per input length instead of issuing the launch chain (Synthesizer /
+        # test.sh turn it on: batch-1 calls are launch-bound)
+        self.use_cuda_graphs = False
         self._reset_parameters()
         if use_weight_norm:
             self.apply_weight_norm()
@@ -120,8 +123,42 @@ class _NativeGenerator(torch.nn.Module):
             self.apply_weight_norm()
         self._bound_key = None
 
-    def state_dict(self, *args, **kwargs):
-        """Reference key set: weight-norm form while it is applied, folded form after remove_weight_norm()."""
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        """Reference key set: weight-norm form while it is applied, folded form after remove_weight_norm().
+        Honours nn.Module's (destination, prefix) protocol, so a generator nested in another Module is saved too."""
+        if args:                                  # legacy positional form: (destination, prefix, keep_vars)
+            destination = args[0]
+            prefix = args[1] if len(args) > 1 else prefix
+        sd = self._own_state_dict()
+        if destination is None:
+            destination = OrderedDict()
+        for k, v in sd.items():
+            destination[prefix + k] = v
+        return destination
+
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for k, v in self._own_state_dict().items():      # a parent Module's state_dict() reaches us through this hook
+            destination[prefix + k] = v
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        own = OrderedDict((k[len(prefix):], v) for k, v in state_dict.items() if k.startswith(prefix))
+        try:
+            res = self.load_state_dict(own, strict=False)
+            missing_keys.extend(prefix + k for k in res.missing_keys)
+            unexpected_keys.extend(prefix + k for k in res.unexpected_keys)
+        except RuntimeError as e:
+            error_msgs.append(str(e))
+
+    def _apply(self, fn, recurse=True):
+        """.to(device) moves the packed weights; dtype casts (.half() / .double()) are refused for them: the kernels read the
+        buffer as float32 (the arithmetic type of this path)."""
+        super()._apply(fn, recurse)
+        if self.packed_weights.dtype != torch.float32:
+            self.packed_weights.data = self.packed_weights.data.float()
+        self._bound_key = None
+        return self
+
+    def _own_state_dict(self):
         sd = OrderedDict()
         for name, shape, _ in self._spec:
             prefix = name[:-len(".weight")] if name.endswith(".weight") else None
@@ -178,6 +215,8 @@ class _NativeGenerator(torch.nn.Module):
 
     def _ensure_bound(self):
         pw = self.packed_weights
+        if pw.dtype != torch.float32:
+            raise _lib.FvError(f"{type(self).__name__}: packed weights are {pw.dtype}; the kernels read float32")
         if not pw.is_cuda:
             raise _lib.FvError(f"{type(self).__name__}: weights are on {pw.device}; this implementation has no CPU "
                                "path — call .to('cuda') first")
@@ -293,6 +332,49 @@ class _NativeGenerator(torch.nn.Module):
             raise RuntimeError(f"expected input [B, {self._cfg.in_channels}, T], got {tuple(x.shape)}")
         return x.detach().contiguous().float()
 
+    # ---- CUDA-graph replay of the launch chain (batch-1 latency path) -----------------------------------------
+    def graphed(self, example, **fwd_kwargs):
+        """Capture ``forward(example, **fwd_kwargs)`` into a CUDA graph and return ``run(x)``, which copies ``x`` into the
+        captured input, replays the whole launch chain (~50-100 dependent kernels) with ONE graph launch and returns the
+        captured outputs (valid until the next ``run``; clone them to keep them).  Same kernels, same plans, same
+        buffers -> bit-identical to the eager call.  The graph is tied to the input shape and to the current weights."""
+        x = self._prep_input(example)
+        static_in = x.clone()
+        cur = torch.cuda.current_stream(x.device)
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():      # warm-up: weight binding, workspace, lazy attributes
+            for _ in range(2):
+                self.forward(static_in, **fwd_kwargs)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        key = self._bound_key
+        with torch.cuda.graph(graph), torch.no_grad():
+            static_out = self.forward(static_in, **fwd_kwargs)
+
+        def run(inp):
+            if self._bound_key != key or self._bound_key is None:
+                raise _lib.FvError("graphed(): the weights changed after capture; capture again")
+            static_in.copy_(inp if inp.shape == static_in.shape else self._prep_input(inp))
+            graph.replay()
+            return static_out
+        run.graph, run.static_input, run.static_output = graph, static_in, static_out
+        return run
+
+    def _graphed_inference(self, x, **fwd_kwargs):
+        """inference() through a per-(shape, kwargs) cache of captured graphs (``use_cuda_graphs``); outputs are cloned."""
+        self._ensure_bound()
+        key = (tuple(x.shape), tuple(sorted(fwd_kwargs.items())), self._bound_key)
+        cache = self.__dict__.setdefault("_graphs", OrderedDict())
+        g = cache.get(key)
+        if g is None:
+            if len(cache) >= 16:
+                cache.popitem(last=False)
+            g = cache[key] = self.graphed(x, **fwd_kwargs)
+        out = g(x)
+        return tuple(o.clone() if o is not None else None for o in out) if isinstance(out, tuple) else out.clone()
+
     def _prep_inference_input(self, c):
         """(T, in_channels) ndarray or tensor -> (1, in_channels, T) on the model device (hifigan.py:111-113)."""
         if not isinstance(c, torch.Tensor):
@@ -360,7 +442,10 @@ class HiFiGANGenerator(_NativeGenerator):
 
     def inference(self, x):
         """[T, 80] ndarray/tensor -> 1-D waveform   (hifigan.py:110-129)"""
-        return self.forward(self._prep_inference_input(x)).squeeze()
+        x = self._prep_inference_input(x)
+        if self.use_cuda_graphs:
+            return self._graphed_inference(self._prep_input(x)).squeeze()
+        return self.forward(x).squeeze()
 
 
 class MultiBandHiFiGANGenerator(_NativeGenerator):
@@ -403,13 +488,17 @@ class MultiBandHiFiGANGenerator(_NativeGenerator):
 
     def inference(self, x):
         """[T, 80] -> 1-D waveform through PQMF synthesis   (multiband_hifigan.py:118-137)"""
-        _, wav = self.forward(self._prep_inference_input(x), synthesize=True)
+        x = self._prep_inference_input(x)
+        if self.use_cuda_graphs:
+            _, wav = self._graphed_inference(self._prep_input(x), synthesize=True)
+        else:
+            _, wav = self.forward(x, synthesize=True)
         return wav.squeeze()
 
 
 def _fill_melgan(cfg, kind, in_channels, out_channels, kernel_size, channels, upsample_scales, stack_kernel_size,
                  stacks, use_final_nonlinear_activation, use_causal_conv, nonlinear_activation,
-                 nonlinear_activation_params, pad):
+                 nonlinear_activation_params, pad, bias=True):
     if nonlinear_activation != "LeakyReLU" or pad != "ReflectionPad1d":
         raise NotImplementedError("only LeakyReLU + ReflectionPad1d (the shipped configs) are implemented")
     if not use_causal_conv:
@@ -420,12 +509,14 @@ def _fill_melgan(cfg, kind, in_channels, out_channels, kernel_size, channels, up
     cfg.use_causal_conv = 1 if use_causal_conv else 0
     if len(channels) != len(upsample_scales) + 1:
         raise ValueError("channels must have len(upsample_scales) + 1 entries")
-    slope = float(nonlinear_activation_params.get("negative_slope", 0.01))
-    if abs(slope - 0.2) > 1e-12:
-        raise NotImplementedError("negative_slope other than 0.2 is not wired through the C ABI yet")
+    slope = float(nonlinear_activation_params.get("negative_slope", 0.01))   # nn.LeakyReLU's own default
+    if not (0.0 <= slope <= 1.0):
+        raise NotImplementedError("negative_slope outside [0, 1] is not implemented (LeakyReLU as max(x, slope*x))")
+    cfg.negative_slope_set = 1
+    cfg.negative_slope = slope
     cfg.kind = kind
     cfg.in_channels = in_channels
-    cfg.bias = 1
+    cfg.bias = 1 if bias else 0
     cfg.num_upsamples = len(upsample_scales)
     _set_arr(cfg.upsample_rates, upsample_scales)
     _set_arr(cfg.upsample_kernel_sizes, [2 * s for s in upsample_scales])   # melgan.py:81
@@ -448,31 +539,29 @@ class MelGANGenerator(_NativeGenerator):
                  upsample_scales=[10, 6, 2, 2], stack_kernel_size=3, stacks=3, nonlinear_activation="LeakyReLU",
                  nonlinear_activation_params={"negative_slope": 0.2}, pad="ReflectionPad1d", pad_params={},
                  use_final_nonlinear_activation=True, use_weight_norm=True, use_causal_conv=False):
-        if not bias:
-            raise NotImplementedError("bias=False MelGAN is not wired (no shipped config uses it)")
         cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_MELGAN, in_channels, out_channels, kernel_size, channels,
                            upsample_scales, stack_kernel_size, stacks, use_final_nonlinear_activation,
-                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad)
+                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad, bias=bias)
         super().__init__(cfg, use_weight_norm=use_weight_norm)
         self.pqmf = None
 
-    def forward(self, c):
-        """[B, 80, T] -> [B, prod(scales) * T]   (melgan.py:125-136; channel 0 of the 1-channel output)"""
+    def forward(self, c, all_channels=False):
+        """[B, 80, T] -> [B, prod(scales) * T]   (melgan.py:125-136; channel 0 of the 1-channel output).
+        ``all_channels=True`` returns the whole [B, out_channels, L] tensor (what ``inference`` squeezes, melgan.py:172-185)."""
         c = self._prep_input(c)
         B, _, T = c.shape
         Lo = self.out_length(T)
         oc = self._cfg.out_channels
         out = torch.empty(B, oc, Lo, device=c.device, dtype=torch.float32)
         self._run(c, out, None)
-        return out[:, 0, :]
+        return out if all_channels else out[:, 0, :]
 
     def inference(self, c):
         """[T, 80] -> waveform   (melgan.py:172-185)"""
         c = self._prep_input(self._prep_inference_input(c))
-        Lo = self.out_length(c.shape[2])
-        out = torch.empty(1, self._cfg.out_channels, Lo, device=c.device, dtype=torch.float32)
-        self._run(c, out, None)
-        return out.squeeze()
+        if self.use_cuda_graphs:
+            return self._graphed_inference(c, all_channels=True).squeeze()
+        return self.forward(c, all_channels=True).squeeze()
 
 
 class BasisMelGANGenerator(_NativeGenerator):
@@ -485,13 +574,13 @@ class BasisMelGANGenerator(_NativeGenerator):
                  nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.2},
                  pad="ReflectionPad1d", pad_params={}, use_final_nonlinear_activation=True, use_weight_norm=True,
                  use_causal_conv=False, transposedconv=True, lastlinear=False):
-        if not bias:
-            raise NotImplementedError("bias=False Basis-MelGAN is not wired (no shipped config uses it)")
+        if not bias and lastlinear:
+            raise NotImplementedError("lastlinear=True with bias=False: the folded eval-mode BatchNorm needs the bias slot")
         # without LastLinear the predictor's width is channels[-1] (basis_melgan.py:70-121 never uses out_channels)
         width = out_channels if lastlinear else channels[-1]
         cfg = _fill_melgan(_lib.FvConfig(), _lib.FV_BASIS_MELGAN, in_channels, width, kernel_size, channels,
                            upsample_scales, stack_kernel_size, stacks, use_final_nonlinear_activation,
-                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad)
+                           use_causal_conv, nonlinear_activation, nonlinear_activation_params, pad, bias=bias)
         cfg.basis_L = L
         cfg.lastlinear = 1 if lastlinear else 0
         # LastLinear (modules.py:116-132) sits at index 2 + sum(2 + stacks) of the nn.Sequential
@@ -572,8 +661,8 @@ class BasisMelGANGenerator(_NativeGenerator):
                 raise RuntimeError(f"Error(s) in loading state_dict for {type(self).__name__}: missing keys {missing_bn}")
         return super().load_state_dict(state_dict, strict)
 
-    def state_dict(self, *args, **kwargs):
-        sd = super().state_dict(*args, **kwargs)
+    def _own_state_dict(self):
+        sd = super()._own_state_dict()
         if getattr(self, "_ll", None):
             if self._ll_folded:               # report checkpoint-form (un-folded) LastLinear parameters
                 for n in self._LL_NAMES:
@@ -583,11 +672,17 @@ class BasisMelGANGenerator(_NativeGenerator):
                 sd[k] = v.clone()
         return sd
 
-    def forward(self, c, return_weight=True):
+    def forward(self, c, return_weight=True, _inference=False):
         """[B, 80, T] -> (est_source - zero_est [B, 16T*15], weight - zero_weight [B, 16T, C])
-        (basis_melgan.py:140-162).  The input-independent zero pass rides along as one extra utterance."""
+        (basis_melgan.py:140-162).  The input-independent zero pass rides along as one extra utterance.
+        ``_inference=True`` (used by ``inference``): one pass, no subtraction, untruncated [B, (16T+1)*15]."""
         c = self._prep_input(c)
         B, _, T = c.shape
+        if _inference:
+            n = self.out_length(T, _lib.FV_FWD_BASIS_INFERENCE)
+            out = torch.empty(B, n, device=c.device, dtype=torch.float32)
+            self._run(c, out, None, flags=_lib.FV_FWD_BASIS_INFERENCE)
+            return out
         n = self.out_length(T)
         hop = self.L // 2
         est = torch.empty(B, n, device=c.device, dtype=torch.float32)
@@ -599,25 +694,39 @@ class BasisMelGANGenerator(_NativeGenerator):
     def inference(self, c):
         """[T, 80] -> untruncated (16T+1)*15 samples, no bias subtraction   (basis_melgan.py:196-208)"""
         c = self._prep_input(self._prep_inference_input(c))
-        n = self.out_length(c.shape[2], _lib.FV_FWD_BASIS_INFERENCE)
-        out = torch.empty(1, n, device=c.device, dtype=torch.float32)
-        self._run(c, out, None, flags=_lib.FV_FWD_BASIS_INFERENCE)
-        return out.squeeze()
+        if self.use_cuda_graphs:
+            return self._graphed_inference(c, return_weight=False, _inference=True).squeeze()
+        return self.forward(c, return_weight=False, _inference=True).squeeze()
 
     def test(self, weight):
         """basis_signal(weight): Linear + overlap-add on a given weight tensor (basis_melgan.py:210-212)."""
-        raise NotImplementedError("use forward()/inference(); the standalone basis layer is exposed as "
-                                  "fv_overlap_add in the C ABI")
+        self._ensure_bound()
+        w = weight.detach().to(self.device).float().contiguous()
+        if w.dim() != 3 or w.shape[2] != self._cfg.out_channels:
+            raise RuntimeError(f"expected weight [B, frames, {self._cfg.out_channels}], got {tuple(w.shape)}")
+        B, n, Cw = w.shape
+        hop = self.L // 2
+        w = w.transpose(1, 2).contiguous()                 # the kernels read [B, C, frames]
+        out = torch.empty(B, (n + 1) * hop, device=w.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().fv_basis_signal(self._handle, _lib.ptr(w), B, n, _lib.ptr(out),
+                                                  1 if self.use_tensor_cores else 0, _lib.current_stream_ptr()),
+                       "fv_basis_signal")
+        return out
 
 
 def build_generator(model_name: str, config: dict):
-    """Construct a generator from a reference YAML dict exactly as bin/synthesize.py:25-68 does."""
+    """Construct a generator from a reference YAML dict exactly as bin/synthesize.py:25-68 does.  Superset: the MelGAN-family
+    constructor kwargs the reference CLI never forwards (`bias`, `nonlinear_activation_params`,
+    `use_final_nonlinear_activation`, melgan.py:20-36) are passed on when the dict carries them."""
+    extra = {k: config[k] for k in ("bias", "nonlinear_activation_params", "use_final_nonlinear_activation") if k in config}
     if model_name == "melgan":
         return MelGANGenerator(in_channels=config["in_channels"], out_channels=config["out_channels"],
                                kernel_size=config["kernel_size"], channels=config["channels"],
                                upsample_scales=config["upsample_scales"],
                                stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
-                               use_weight_norm=config["use_weight_norm"], use_causal_conv=config["use_causal_conv"])
+                               use_weight_norm=config["use_weight_norm"], use_causal_conv=config["use_causal_conv"],
+                               **extra)
     if model_name == "hifigan":
         cls = HiFiGANGenerator
     elif model_name == "multiband-hifigan":
@@ -632,7 +741,7 @@ def build_generator(model_name: str, config: dict):
                                     use_weight_norm=config["use_weight_norm"],
                                     use_causal_conv=config["use_causal_conv"],
                                     transposedconv=config["transposedconv"],
-                                    lastlinear=config.get("lastlinear", False))
+                                    lastlinear=config.get("lastlinear", False), **extra)
     else:
         raise Exception("no model find!")
     return cls(resblock_kernel_sizes=config["resblock_kernel_sizes"], upsample_rates=config["upsample_rates"],

@@ -66,6 +66,8 @@ class Synthesizer:
         self.L = config.get("L")
         model.eval()
         model.remove_weight_norm()
+        # batch-1 calls are launch-bound (~50-100 dependent kernels): inference() replays a CUDA graph captured per length
+        model.use_cuda_graphs = os.environ.get("FV_CUDA_GRAPHS", "1") != "0"
         return model
 
     def zero_input_bias(self, frames: int) -> torch.Tensor:

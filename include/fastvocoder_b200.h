@@ -59,7 +59,7 @@ extern "C" {
 typedef struct fv_config {
   int32_t kind;                         /* FV_HIFIGAN ... */
   int32_t in_channels;                  /* 80 mel bins */
-  int32_t bias;                         /* conv bias on/off (HiFi `bias`; MelGAN family always 1) */
+  int32_t bias;                         /* conv bias on/off (`bias` kwarg of all four generators) */
   int32_t num_upsamples;                /* len(upsample_rates) / len(upsample_scales) */
   int32_t upsample_rates[FV_MAX_STAGES];
   int32_t upsample_kernel_sizes[FV_MAX_STAGES]; /* HiFi: upsample_kernel_sizes; MelGAN: 2*scale */
@@ -94,7 +94,10 @@ typedef struct fv_config {
                                            LReLU.2 -> BN -> 1x1(C->out_channels).  Inference (eval-mode) semantics: the
                                            host folds each BatchNorm1d's running statistics into the 1x1 conv that follows
                                            it, so the packed `melgan.N.linear_{1,2}.{weight,bias}` are the folded ones */
-  int32_t reserved[5];
+  int32_t negative_slope_set;           /* MelGAN family: 1 = `negative_slope` below replaces the default 0.2 of           */
+  float negative_slope;                 /* nonlinear_activation_params (melgan.py:30; LeakyReLU of every stack / upsample / */
+                                        /* LastLayer; LastLinear keeps its hard-coded 0.2, modules.py:119)                  */
+  int32_t reserved[3];
 } fv_config;
 
 typedef struct fv_handle fv_handle;
@@ -170,13 +173,14 @@ int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops)
 /* ---- per-op entry points (unit parity tests; reference layouts, weights passed raw) ---------------
  * All pointers are device pointers.  `pad_mode`: 0 zero, 1 reflect.  `pre_slope` < 0 disables the
  * LeakyReLU applied to the input before the convolution (0 = ReLU).  `residual` may be NULL.
- * `use_tc` != 0 routes through the tcgen05 path when the shape is eligible (fv_resblock1: 2 = fused-unit kernel).
+ * `use_tc` != 0 routes through the tcgen05 path when the shape is eligible (fv_resblock1: 2 = fused-unit kernel,
+ * 3 = fused units chained through the TMA-fed split fp16 hi/lo activation format).
  *
  * fv_conv1d            <- torch.nn.Conv1d call sites (modules.py:193-220,364,366,377; hifigan.py:93,105)
  * fv_conv_transpose1d  <- torch.nn.ConvTranspose1d call sites (hifigan.py:39-44, melgan.py:77-85)
  * fv_resblock1         <- ResBlock1.forward        modules.py:223-230
  * fv_residual_stack    <- ResidualStack.forward    modules.py:372-382
- * fv_overlap_add       <- overlap_and_add          modules.py:34-73 (frame_length == 2*frame_step)
+ * fv_overlap_add       <- overlap_and_add          modules.py:34-73 (any frame_length / frame_step; out [B, (frames-1)*step + length])
  * fv_pqmf_synthesis    <- PQMF.synthesis           pqmf.py:121-135
  * fv_pqmf_analysis     <- PQMF.analysis            pqmf.py:108-119
  * fv_encode_16bits     <- data/audio.py:12-14      (save_wav's peak-normalise + int16 cast) */
@@ -192,6 +196,10 @@ int fv_resblock1(const float* x, const float* const* w1, const float* const* b1,
 int fv_residual_stack(const float* c, const float* w_dil, const float* b_dil, const float* w_1x1,
                       const float* b_1x1, const float* w_skip, const float* b_skip, float* y, float* scratch,
                       int B, int C, int L, int K, int dilation, int use_tc, void* stream);
+/* BasisMelGANGenerator.test(weight) / BasisSignalLayer.forward   basis_melgan.py:210-212, modules.py:255-267
+ *   weight_bcl [B, C, frames] (channels first — the Python binding transposes the reference's [B, frames, C]),
+ *   out [B, (frames+1)*hop]: Linear(C -> L, no bias, no activation) + overlap_and_add(hop = L/2) of the bound handle. */
+int fv_basis_signal(fv_handle* h, const float* weight_bcl, int B, int frames, float* out, int use_tc, void* stream);
 int fv_overlap_add(const float* frames, int B, int num_frames, int frame_length, int frame_step, float* out,
                    void* stream);
 int fv_pqmf_synthesis(const float* x, const float* synthesis_filter, int B, int subbands, int taps, int Lband,

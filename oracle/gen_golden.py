@@ -100,12 +100,30 @@ VARIANTS = {
     "basis-melgan-upsamplelayer": ("basis-melgan", "conf/basis-melgan/light.yaml", {"transposedconv": False}, (2, 24)),
     "basis-melgan-causal-lastlinear": ("basis-melgan", "conf/basis-melgan/light.yaml",
                                        {"use_causal_conv": True, "lastlinear": True, "out_channels": 128}, (2, 24)),
+    # round 2: ResBlock2 with the constructor-default THREE-entry dilation lists (only dilation[0..1] are used,
+    # modules.py:233-245), and the MelGAN-family kwargs bin/synthesize.py never passes (bias, negative_slope, final activation)
+    "hifigan-light-resblock2-dil3": ("hifigan", "conf/hifigan/light.yaml", {"resblock_type": "2"}, (2, 24)),
+    "melgan-nobias-slope01": ("melgan", "conf/melgan/original.yaml",
+                              {"bias": False, "nonlinear_activation_params": {"negative_slope": 0.1},
+                               "use_final_nonlinear_activation": False}, (2, 12)),
+    "basis-melgan-nobias-nofinal": ("basis-melgan", "conf/basis-melgan/light.yaml",
+                                    {"bias": False, "nonlinear_activation_params": {"negative_slope": 0.3},
+                                     "use_final_nonlinear_activation": False}, (2, 24)),
 }
+EXTRA_KW = ("bias", "nonlinear_activation_params", "use_final_nonlinear_activation")
 
 
 def build_variant(model_name, config):
+    extra = {k: config[k] for k in EXTRA_KW if k in config}     # constructor kwargs the CLI never passes
+    if model_name == "melgan" and extra:
+        return MelGANGenerator(in_channels=config["in_channels"], out_channels=config["out_channels"],
+                               kernel_size=config["kernel_size"], channels=config["channels"],
+                               upsample_scales=config["upsample_scales"],
+                               stack_kernel_size=config["stack_kernel_size"], stacks=config["stacks"],
+                               use_weight_norm=config["use_weight_norm"],
+                               use_causal_conv=config["use_causal_conv"], **extra)
     if model_name == "basis-melgan":    # bin/synthesize.py never passes `lastlinear`; the class does (basis_melgan.py:41)
-        return BasisMelGANGenerator(basis_signal_weight=torch.zeros(config["L"], config["out_channels"]).float(),
+        return BasisMelGANGenerator(basis_signal_weight=torch.zeros(config["L"], config["out_channels"]).float(), **extra,
                                     L=config["L"], in_channels=config["in_channels"],
                                     out_channels=config["out_channels"], kernel_size=config["kernel_size"],
                                     channels=config["channels"], upsample_scales=config["upsample_scales"],
@@ -158,7 +176,13 @@ def variants_main():
         specs = json.load(f)
     with open(os.path.join(OUT, "manifest.json")) as f:
         manifest = json.load(f)
+    only = None
+    for a in sys.argv:
+        if a.startswith("--only="):          # add new variants without rewriting the existing fixture files
+            only = set(a[len("--only="):].split(","))
     for key, (model_name, ypath, over, (B, T)) in VARIANTS.items():
+        if only is not None and key not in only:
+            continue
         with open(os.path.join(REF, ypath)) as f:
             config = yaml.load(f, Loader=yaml.Loader)
         config.update(over)

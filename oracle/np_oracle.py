@@ -146,15 +146,15 @@ def residual_stack(c, params, prefix, kernel_size, dilation, slope=0.2, use_caus
     Causal (modules.py:355-361): stack = LReLU -> CausalConv1d -> LReLU -> Conv1d 1x1 (keys stack.1.conv / stack.3)."""
     h = leaky_relu(c, slope)
     if use_causal_conv:
-        h = causal_conv1d(h, params[f"{prefix}.stack.1.conv.weight"], params[f"{prefix}.stack.1.conv.bias"], dilation)
+        h = causal_conv1d(h, params[f"{prefix}.stack.1.conv.weight"], params.get(f"{prefix}.stack.1.conv.bias"), dilation)
         h = leaky_relu(h, slope)
-        h = conv1d(h, params[f"{prefix}.stack.3.weight"], params[f"{prefix}.stack.3.bias"])
+        h = conv1d(h, params[f"{prefix}.stack.3.weight"], params.get(f"{prefix}.stack.3.bias"))
     else:
         h = reflection_pad1d(h, (kernel_size - 1) // 2 * dilation)
-        h = conv1d(h, params[f"{prefix}.stack.2.weight"], params[f"{prefix}.stack.2.bias"], dilation=dilation)
+        h = conv1d(h, params[f"{prefix}.stack.2.weight"], params.get(f"{prefix}.stack.2.bias"), dilation=dilation)
         h = leaky_relu(h, slope)
-        h = conv1d(h, params[f"{prefix}.stack.4.weight"], params[f"{prefix}.stack.4.bias"])
-    s = conv1d(c, params[f"{prefix}.skip_layer.weight"], params[f"{prefix}.skip_layer.bias"])
+        h = conv1d(h, params[f"{prefix}.stack.4.weight"], params.get(f"{prefix}.stack.4.bias"))
+    s = conv1d(c, params[f"{prefix}.skip_layer.weight"], params.get(f"{prefix}.skip_layer.bias"))
     return h + s
 
 
@@ -180,7 +180,7 @@ def last_layer(x, params, prefix, kernel_size, slope=0.2):
     """LastLayer.forward, modules.py:85-89: LReLU -> ReflectionPad1d((k-1)//2) -> Conv1d."""
     x = leaky_relu(x, slope)
     x = reflection_pad1d(x, (kernel_size - 1) // 2)
-    return conv1d(x, params[f"{prefix}.conv.weight"], params[f"{prefix}.conv.bias"])
+    return conv1d(x, params[f"{prefix}.conv.weight"], params.get(f"{prefix}.conv.bias"))
 
 
 def overlap_and_add(signal, frame_step):
@@ -315,6 +315,12 @@ def mb_hifigan_inference(params, cfg, c):
     return np.squeeze(pqmf_synthesis(_hifigan_trunk(params, cfg, c.T[None])))
 
 
+def mel_slope(cfg):
+    """LeakyReLU slope of the MelGAN family: nonlinear_activation_params (default {"negative_slope": 0.2}, melgan.py:30;
+    a dict without the key falls back to nn.LeakyReLU's own default 0.01)."""
+    return float(cfg.get("nonlinear_activation_params", {"negative_slope": 0.2}).get("negative_slope", 0.01))
+
+
 def _melgan_body(params, cfg, c, n_prefix="melgan"):
     """The nn.Sequential built in melgan.py:66-112 / basis_melgan.py:70-125 up to (excluding) the final layer."""
     ch = cfg["channels"]
@@ -323,11 +329,12 @@ def _melgan_body(params, cfg, c, n_prefix="melgan"):
     stacks = cfg["stacks"]
     sk = cfg["stack_kernel_size"]
     idx = 0
+    slope = mel_slope(cfg)
     x = reflection_pad1d(c, (ksize - 1) // 2)                                   # melgan.0
     x = conv1d(x, params[f"{n_prefix}.1.weight"], params.get(f"{n_prefix}.1.bias"))  # melgan.1
     idx = 2
     for i, u in enumerate(scales):
-        x = leaky_relu(x, 0.2)                                                  # idx
+        x = leaky_relu(x, slope)                                                # idx
         if cfg.get("transposedconv", True) == False and "L" in cfg:   # noqa: E712  basis_melgan.py:82-88 only
             x = upsample_layer(x, params[f"{n_prefix}.{idx + 1}.conv.weight"],
                                params.get(f"{n_prefix}.{idx + 1}.conv.bias"), u, u)
@@ -336,7 +343,7 @@ def _melgan_body(params, cfg, c, n_prefix="melgan"):
                                  stride=u, padding=u // 2 + u % 2, output_padding=u % 2)
         idx += 2
         for j in range(stacks):
-            x = residual_stack(x, params, f"{n_prefix}.{idx}", sk, sk ** j,
+            x = residual_stack(x, params, f"{n_prefix}.{idx}", sk, sk ** j, slope=slope,
                                use_causal_conv=cfg.get("use_causal_conv", False))
             idx += 1
     return x, idx
@@ -345,7 +352,7 @@ def _melgan_body(params, cfg, c, n_prefix="melgan"):
 def melgan_forward(params, cfg, c):
     """MelGANGenerator.forward, melgan.py:125-136: [B,80,T] -> [B, prod(scales)*T]."""
     x, idx = _melgan_body(params, cfg, c)
-    x = last_layer(x, params, f"melgan.{idx}", cfg["kernel_size"])
+    x = last_layer(x, params, f"melgan.{idx}", cfg["kernel_size"], slope=mel_slope(cfg))
     if cfg.get("use_final_nonlinear_activation", True):
         x = np.tanh(x)
     return x[:, 0, :]

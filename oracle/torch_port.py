@@ -55,19 +55,23 @@ def upsample_layer(x, w, b, rate, padding):  # modules.py:160-177 (Stretch2d nea
     return F.conv1d(x, w, b, padding=padding)
 
 
-def residual_stack(c, params, prefix, k, d, causal=False):  # modules.py:343-382
-    h = F.leaky_relu(c, 0.2)
+def mel_slope(cfg):  # nonlinear_activation_params default {"negative_slope": 0.2} (melgan.py:30); nn.LeakyReLU default 0.01
+    return float(cfg.get("nonlinear_activation_params", {"negative_slope": 0.2}).get("negative_slope", 0.01))
+
+
+def residual_stack(c, params, prefix, k, d, causal=False, slope=0.2):  # modules.py:343-382
+    h = F.leaky_relu(c, slope)
     if causal:  # CausalConv1d, modules.py:273-297: ReflectionPad1d((k-1)*d) both sides, conv, keep the first T
         T = h.size(2)
         h = F.pad(h, ((k - 1) * d,) * 2, mode="reflect")
         h = F.conv1d(h, params[f"{prefix}.stack.1.conv.weight"], _p(params, f"{prefix}.stack.1.conv.bias"),
                      dilation=d)[:, :, :T]
-        h = F.leaky_relu(h, 0.2)
+        h = F.leaky_relu(h, slope)
         h = F.conv1d(h, params[f"{prefix}.stack.3.weight"], _p(params, f"{prefix}.stack.3.bias"))
     else:
         h = F.pad(h, ((k - 1) // 2 * d,) * 2, mode="reflect")
         h = F.conv1d(h, params[f"{prefix}.stack.2.weight"], _p(params, f"{prefix}.stack.2.bias"), dilation=d)
-        h = F.leaky_relu(h, 0.2)
+        h = F.leaky_relu(h, slope)
         h = F.conv1d(h, params[f"{prefix}.stack.4.weight"], _p(params, f"{prefix}.stack.4.bias"))
     return h + F.conv1d(c, params[f"{prefix}.skip_layer.weight"], _p(params, f"{prefix}.skip_layer.bias"))
 
@@ -159,8 +163,9 @@ def _melgan_body(params, cfg, c):  # melgan.py:66-112, basis_melgan.py:70-125
     x = F.pad(c, ((k - 1) // 2,) * 2, mode="reflect")
     x = F.conv1d(x, params["melgan.1.weight"], _p(params, "melgan.1.bias"))
     idx = 2
+    slope = mel_slope(cfg)
     for u in cfg["upsample_scales"]:
-        x = F.leaky_relu(x, 0.2)
+        x = F.leaky_relu(x, slope)
         if cfg.get("transposedconv", True) == False and "L" in cfg:   # noqa: E712  basis_melgan.py:82-88 only
             x = upsample_layer(x, params[f"melgan.{idx + 1}.conv.weight"], _p(params, f"melgan.{idx + 1}.conv.bias"), u, u)
         else:
@@ -169,7 +174,7 @@ def _melgan_body(params, cfg, c):  # melgan.py:66-112, basis_melgan.py:70-125
         idx += 2
         for j in range(cfg["stacks"]):
             x = residual_stack(x, params, f"melgan.{idx}", cfg["stack_kernel_size"], cfg["stack_kernel_size"] ** j,
-                               causal=cfg.get("use_causal_conv", False))
+                               causal=cfg.get("use_causal_conv", False), slope=slope)
             idx += 1
     return x, idx
 
@@ -177,17 +182,21 @@ def _melgan_body(params, cfg, c):  # melgan.py:66-112, basis_melgan.py:70-125
 def melgan_forward(params, cfg, c):  # melgan.py:125-136
     x, idx = _melgan_body(params, cfg, c)
     k = cfg["kernel_size"]
-    x = F.leaky_relu(x, 0.2)
+    x = F.leaky_relu(x, mel_slope(cfg))
     x = F.pad(x, ((k - 1) // 2,) * 2, mode="reflect")
     x = F.conv1d(x, params[f"melgan.{idx}.conv.weight"], _p(params, f"melgan.{idx}.conv.bias"))
-    return torch.tanh(x)[:, 0, :]
+    if cfg.get("use_final_nonlinear_activation", True):   # melgan.py:108-110
+        x = torch.tanh(x)
+    return x[:, 0, :]
 
 
 def _basis_pass(params, cfg, c):
     x, idx = _melgan_body(params, cfg, c)
     if cfg.get("lastlinear", False):  # basis_melgan.py:117-118
         x = last_linear(x, params, f"melgan.{idx}")
-    weight = torch.relu(x).contiguous().transpose(1, 2)
+    if cfg.get("use_final_nonlinear_activation", True):   # basis_melgan.py:120-121
+        x = torch.relu(x)
+    weight = x.contiguous().transpose(1, 2)
     est = overlap_and_add(F.linear(weight, params["basis_signal.layer.weight"]), cfg["L"] // 2)
     return est, weight
 

@@ -14,7 +14,9 @@ MODEL_KEYS = ["hifigan-light", "hifigan-large", "multiband-hifigan-light", "mult
               "melgan-original", "basis-melgan-light"]
 # non-default architecture switches, goldens from the reference classes with the switch turned on
 VARIANT_KEYS = ["hifigan-light-upsamplelayer", "hifigan-light-resblock2", "multiband-hifigan-light-upsamplelayer",
-                "melgan-causal", "basis-melgan-upsamplelayer", "basis-melgan-causal-lastlinear"]
+                "melgan-causal", "basis-melgan-upsamplelayer", "basis-melgan-causal-lastlinear",
+                # round 2: ResBlock2 with 3-entry dilation lists; MelGAN family bias=False / negative_slope / no final activation
+                "hifigan-light-resblock2-dil3", "melgan-nobias-slope01", "basis-melgan-nobias-nofinal"]
 ALL_KEYS = MODEL_KEYS + VARIANT_KEYS
 
 

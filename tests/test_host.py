@@ -211,3 +211,43 @@ def test_variant_output_lengths(specs):
     g = np.load(os.path.join(GOLDEN, "model_multiband-hifigan-light-upsamplelayer.npz"))
     m = build_generator("multiband-hifigan", dict(specs["multiband-hifigan-light-upsamplelayer"]["config"]))
     assert m.out_length(g["mel"].shape[-1]) == g["forward0_f32"].shape[-1]
+
+
+# ---- round 2: advisor findings -----------------------------------------------------------------------------------
+def test_resblock_conv_counts_and_type_comparison_follow_the_reference_constructors():
+    """modules.py:190-251 hard-codes 3 (convs1, convs2) pairs for ResBlock1 and 2 convs for ResBlock2 whatever the length of
+    the dilation list; hifigan.py:28 compares `resblock_type == '1'` (an int 1 selects ResBlock2)."""
+    from fastvocoder_b200 import HiFiGANGenerator
+    m2 = HiFiGANGenerator(resblock_type="2")                       # constructor-default dilations [[1, 3, 5]] * 3
+    keys = {n for n, _, _ in m2._spec}
+    assert "resblocks.0.convs.1.weight" in keys and "resblocks.0.convs.2.weight" not in keys
+    assert not any(".convs1." in k for k in keys)
+    m_int = HiFiGANGenerator(resblock_type=1)                      # unquoted YAML 1 -> ResBlock2, as in the reference
+    assert any(".convs." in n for n, _, _ in m_int._spec) and not any(".convs1." in n for n, _, _ in m_int._spec)
+    m1 = HiFiGANGenerator(resblock_dilation_sizes=[[1, 3, 5, 7]] * 3)   # the 4th entry is ignored
+    assert "resblocks.0.convs1.2.weight" in {n for n, _, _ in m1._spec}
+    assert "resblocks.0.convs1.3.weight" not in {n for n, _, _ in m1._spec}
+    with pytest.raises(IndexError):
+        HiFiGANGenerator(resblock_dilation_sizes=[[1, 3]] * 3)     # dilation[2] raises in ResBlock1.__init__
+
+
+def test_nested_generator_state_dict_round_trips_and_dtype_casts_keep_float32():
+    import torch
+    from fastvocoder_b200 import HiFiGANGenerator
+
+    class Wrapper(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gen = HiFiGANGenerator(upsample_initial_channel=32)
+
+    w = Wrapper()
+    sd = w.state_dict()
+    assert "gen.conv_pre.weight_g" in sd and "gen.ups.0.weight_v" in sd
+    w2 = Wrapper()
+    res = w2.load_state_dict(sd)
+    assert not res.missing_keys and not res.unexpected_keys
+    for (k, a), (_, b) in zip(w.gen.state_dict().items(), w2.gen.state_dict().items()):
+        assert torch.equal(a, b), k
+    w2.half()
+    assert w2.gen.packed_weights.dtype == torch.float32
+    assert "pre.conv_pre.weight_g" in w.gen.state_dict(prefix="pre.")
