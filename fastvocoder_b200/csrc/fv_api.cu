@@ -280,10 +280,20 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       long long l = lens_host[b];
       if (l <= 0 || l > T || (!m.is_hifi() && l <= (c.pre_kernel_size - 1) / 2))
         return fail(FV_EINVAL, "lens[%d] = %lld out of range for T = %d", b, l, T);
+      if (c.kind == FV_MELGAN && m.len_after((int)l, (int)m.stages.size() - 1) <= (c.post_kernel_size - 1) / 2)
+        return fail(FV_EINVAL, "lens[%d] = %lld too short for the LastLayer reflection pad", b, l);
       hl[b] = (int)l;
       for (size_t s = 0; s < m.stages.size(); ++s) {
         l = Model::convt_out_len(m.layers[m.stages[s].up], l);
         if (l <= 0) return fail(FV_EINVAL, "lens[%d] too short for this architecture", b);
+        // ReflectionPad1d of the widest ResidualStack of this stage needs pad < length (the reference raises there)
+        for (const Stack& sk : m.stages[s].stacks) {
+          const Layer& dc = m.layers[sk.dil_conv];
+          const long long pad = dc.causal ? (long long)(dc.K - 1) * dc.dil : (long long)(dc.K - 1) / 2 * dc.dil;
+          if (pad >= l)
+            return fail(FV_EINVAL, "lens[%d] = %d too short: stage %d has %lld samples but a reflection pad of %lld", b,
+                        (int)lens_host[b], (int)s, l, pad);
+        }
         hl[(s + 1) * B + b] = (int)l;
       }
     }

@@ -51,7 +51,6 @@ struct Layer {
   // derived GEMM view
   int N = 0, Kd = 0;
   int64_t wd_offset = 0;  // float offset of the [Cin][Kd][N] image in the derived buffer
-  double macs_per_out_pos() const { return 0; }
 };
 
 struct ResUnit {  // ResBlock1 unit (conv1 dilated, conv2) or ResBlock2 unit (conv only; c2 = -1)

@@ -286,6 +286,9 @@ __device__ __forceinline__ float lrelu01(float v, float slope) { return fmaxf(v,
 #ifndef FV_PACKED_F32
 #define FV_PACKED_F32 0
 #endif
+#ifndef FV_AB_OLD_LD
+#define FV_AB_OLD_LD 0   // A/B switch: 1 = one tcgen05.wait::ld per 16-column TMEM load in the fused-unit epilogues
+#endif
 #if FV_PACKED_F32
 // (a + b) + c on two lanes
 __device__ __forceinline__ float2 add3_x2(float a0, float a1, float b0, float b1, float c0, float c1) {
@@ -1101,7 +1104,6 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const int kblocks = a.K * ksteps;
   const long long w_total = (long long)kblocks * kblock_bytes;
   const long long BUDGET = 225 * 1024;
-  const int need_mt = (a.Lpos + 127) / 128;
   static const int force_dual = getenv("FV_TC2_DUAL") ? atoi(getenv("FV_TC2_DUAL")) : -1;   // tuning knob: 0 / 1
   if ((a.res != nullptr || a.acc_mode != ACC_STORE) && (a.out_layout != OUT_BCL || a.post_tanh)) return false;
   {  // the kernels index inside one utterance's input / output plane with 32-bit element offsets
@@ -1123,6 +1125,16 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   //   epilogue: 0.34 clk per output element, +0.47 with a residual read, +0.74 with the MRF read-modify-write
   //     (latency-bound global accesses of 4 warps); it overlaps the MMAs only with two accumulator sets.
   const int ck_opts[4] = {a.Cin, 128, 64, 32};
+  // The K-chunk size fixes the ORDER in which the tensor core accumulates (chunk-major vs tap-major), i.e. the rounding of
+  // every output.  It is therefore chosen from the layer shape alone (phase 0: canonical problem size) and only the
+  // scheduling parameters (tile height, buffering, ring depth) follow the actual batch / length (phase 1) — a batched call
+  // and per-utterance calls produce bit-identical samples whatever plans they get.
+  int ck_fixed = 0;
+  for (int phase = 0; phase < 2; ++phase) {
+  const int pl_Lpos = phase == 0 ? (1 << 20) : a.Lpos;
+  const int pl_B = phase == 0 ? 8 : a.B;
+  const int need_mt = (pl_Lpos + 127) / 128;
+  best = Cand{0, 0, 0, 0, 0, 0, 0, -1.0};
   for (int df = 2; df >= 1; --df) {
     if (df == 2 && NT > 128) continue;
     if (force_dual >= 0 && NT <= 128 && (df == 2) != (force_dual != 0)) continue;
@@ -1136,6 +1148,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
     for (int cki = 0; cki < 4; ++cki) {
       const int ck = ck_opts[cki];
       if (ck > a.Cin || a.Cin % ck || ck % 16 || (cki > 0 && ck == a.Cin)) continue;
+      if (phase == 1 && ck != ck_fixed) continue;
       const int nck = a.Cin / ck, kpc = ck / 16;
       int kbps = 16384 / kblock_bytes;
       if (kbps < 1) kbps = 1;
@@ -1170,12 +1183,12 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
               double t_tile = (a_st == 2) ? std::max(t_core, t_load) : (t_core + t_load);
               t_tile = acc2 ? std::max(t_tile, t_epi) : (t_tile + t_epi);
               t_tile += 3000.0;   // measured fixed cost per tile (barrier hand-offs, pipeline bubbles)
-              const long long tiles = (long long)((a.Lpos + mt * 128 - 1) / (mt * 128)) * a.B;
+              const long long tiles = (long long)((pl_Lpos + mt * 128 - 1) / (mt * 128)) * pl_B;
               long long gx = std::max(1, num_sms / L.n_tiles);
               if (gx > tiles) gx = tiles;
               const long long waves = (tiles + gx - 1) / gx;
               const double tail_eff = (double)tiles / (double)(waves * gx);
-              const double useful = std::min<double>(mt * 128.0, (double)a.Lpos);
+              const double useful = std::min<double>(mt * 128.0, (double)pl_Lpos);
               const double sc = useful / t_tile * tail_eff;
               if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, ck, kbps, df, sc};
             }
@@ -1183,6 +1196,8 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
     }
   }
   if (best.score < 0) return false;
+  ck_fixed = best.ck;
+  }   // phase
   const int dualf = best.dual;
   p.a = a;
   p.NT = NT;
@@ -1226,14 +1241,14 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
 }
 
 inline void tc_apply_env_once() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  const char* e = getenv("FV_WAIT_HINT");
-  if (e) {
-    int v = atoi(e);
-    cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(int));
-  }
+  static std::once_flag once;
+  std::call_once(once, []() {
+    const char* e = getenv("FV_WAIT_HINT");
+    if (e) {
+      int v = atoi(e);
+      cudaMemcpyToSymbol(g_wait_hint, &v, sizeof(int));
+    }
+  });
 }
 
 // FV_PDL=1: launch the tensor-core kernels of the layer chain with programmatic stream serialization (the next
@@ -1290,26 +1305,30 @@ struct StallReport {
 
 inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st) {
   tc_apply_env_once();
+  static std::mutex mu;          // per-device launch attributes: concurrent fv_forward calls on distinct streams are allowed
   static int num_sms[64] = {};
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (!num_sms[dev]) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
-    num_sms[dev] = prop.multiProcessorCount;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!num_sms[dev]) {
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+      num_sms[dev] = prop.multiProcessorCount;
+    }
+    if (!attr_set[dev]) {
+      if (cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return -1;
+      attr_set[dev] = true;
+    }
   }
   Tc2Args p{};
   if (!L.eligible || !L.image || !tc2_plan(a, L, p, num_sms[dev])) return 1;
   p.wimg = L.image;
   const size_t smem = tc2_smem_bytes(p);
-  if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return -1;
-    attr_set[dev] = true;
-  }
   int gx = num_sms[dev] / L.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
@@ -1377,11 +1396,11 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
 // outputs (conv2's halo is recomputed), x rows = 128m + (K-1)*dil.
 // =================================================================================================
 constexpr int TC3_THREADS = (TC2_LOADER_WARPS + TC2_ISSUE_WARPS + 8) * 32;   // + 4 epiA warps + 4 epiB warps
-// Split (TMA-fed) units have no loader warps.  Resident-weight plans: warps 0-3 / 4-7 become a SECOND epiA / epiB group (a
-// TMEM lane quarter is served by two warps that take alternate (chunk, M tile) iterations) and warp 11 — the weight
-// producer, idle once the images are resident; at most 3 issuers then — is the TMA producer.  Streamed-weight plans (warp
-// 11 feeds the ring; issuer-bound anyway): one epilogue group, warp 0 is the TMA producer.  (A 21st warp would put six
-// warps on one SM sub-partition and cap the kernel at 80 registers.)
+// Split (TMA-fed) units have no loader warps: warp 0 is the TMA producer and warps 4-7 are a SECOND epiB group (a TMEM lane
+// quarter is served by two warps that take alternate (chunk, M tile) iterations; epiB — residual loads, activation split,
+// global stores — is the heavier epilogue: 80-96 % busy against 45-60 % for epiA on the k = 3 units).  A 21st warp would put
+// six warps on one SM sub-partition and cap the kernel at 80 registers; taking an issuer warp for the TMA duty leaves an
+// uneven M-tile split (profiles/r02_notes.md).
 
 struct Tc3Args {
   const float* x;      // unit input [B, C, L] (also the residual)
@@ -1484,9 +1503,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
   const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
   const int epi_groups = (IO != IO_F32 && p.epi_groups == 2) ? 2 : 1;
   // epilogue roles: group 0 = warps 12-15 (epiA) / 16-19 (epiB); split mode with two groups: + warps 0-3 / 4-7
-  const bool is_epiA = (warp >= 12 && warp < 16) || (epi_groups == 2 && warp < 4);
+  const bool is_epiA = (warp >= 12 && warp < 16);
   const bool is_epiB = (warp >= 16 && warp < 20) || (epi_groups == 2 && warp >= 4 && warp < 8);
   const int epi_grp = warp < TC2_LOADER_WARPS ? 1 : 0;
+  const int epiA_groups = 1, epiB_groups = epi_groups;
   if (p.pdl) pdl_launch_dependents();
 
   if (tid == 0) {
@@ -1494,13 +1514,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       mbar_init(BAR(0 + s), IO == IO_F32 ? TC2_LOADER_WARPS : 1);   // split mode: one expect_tx arrive + the TMA bytes
       mbar_init(BAR(2 + s), p.n_issuers);
       mbar_init(BAR(4 + s), p.n_issuers);
-      mbar_init(BAR(6 + s), 4 * epi_groups);
+      mbar_init(BAR(6 + s), 4 * epiA_groups);
     }
-    mbar_init(BAR(8), 4 * epi_groups);
-    mbar_init(BAR(9), p.pp ? 4 * epi_groups : p.n_issuers);   // pp: h_full of the odd buffer; else a2_empty
+    mbar_init(BAR(8), 4 * epiA_groups);
+    mbar_init(BAR(9), p.pp ? 4 * epiA_groups : p.n_issuers);   // pp: h_full of the odd buffer; else a2_empty
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(10 + s), p.n_issuers);
-      mbar_init(BAR(12 + s), 4 * epi_groups);
+      mbar_init(BAR(12 + s), 4 * epiB_groups);
     }
     mbar_init(BAR(14), 1);
     for (int s = 0; s < 4; ++s) {
@@ -1548,8 +1568,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       }
       wa.end(p.dbg, 0, lane == 0, it);
   };
-  const int tma_warp = p.w_resident ? TC2_LOADER_WARPS + TC2_ISSUE_WARPS - 1 : 0;
-  if (IO != IO_F32 && !p.w_resident && warp == 0) {
+  if (IO != IO_F32 && warp == 0) {
     tma_producer();
   } else if (IO == IO_F32 && warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
@@ -1636,8 +1655,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
           }
         }
-        __syncwarp();
-        if (IO != IO_F32 && warp == tma_warp) tma_producer();   // split mode: this warp is not an issuer (n_issuers <= 3)
       } else if (wid == TC2_ISSUE_WARPS - 1) {
         // ring producer (n_issuers <= 3 in ring mode): one slot per tap, in the issuers' consumption order
         WaitAcc<DBG> wa;
@@ -1709,6 +1726,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
               tc_fence_after();
               uint64_t bdj = b_tmpl + (uint64_t)(((w1s + (uint32_t)slot * (uint32_t)p.stage_bytes) >> 4) & 0x3FFF);
               uint64_t ad = ad0 + (uint64_t)(j * dil);
+              if (m_tiles <= n_iss) {   // one M tile per issuer: the tight two-UMMA body (issue cost is on the chain's critical path)
+                for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bdj += kb_step16) {
+                  umma_f16_elect(d0, ad, bdj, idesc2, accum);
+                  umma_f16_elect(d0, ad + lo_delta, bdj, idesc, 1u);
+                  accum = 1u;
+                }
+              } else
               for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bdj += kb_step16) {
                 uint64_t a = ad;
                 uint32_t d = d0;
@@ -1835,13 +1859,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             for (int i = 0; i < 16; ++i) b1v[i] = 0.f;
           }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
-            if (epi_groups == 2 && ((c * p.m_tiles + mt) & 1) != epi_grp) continue;   // the quarter's other warp takes it
             const int r = mt * 128 + q * 32 + lane;
             const int gpos = t0 - p2 + r;
             const bool inside = gpos >= 0 && gpos < Lb;
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
+#if FV_AB_OLD_LD
+            tmem_ld16(tcol, rr);
+            tmem_ld16(tcol + (uint32_t)NT, r2);
+#else
             tmem_ld16x2(tcol, tcol + (uint32_t)NT, rr, r2);
+#endif
             uint32_t hp[8], lp[8];
             const uint32_t keep = inside ? 0xffffffffu : 0u;   // rows outside the sequence are conv2's zero padding
 #pragma unroll
@@ -1913,7 +1941,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             for (int i = 0; i < 16; ++i) bias[i] = 0.f;
           }
           for (int mt = 0; mt < p.m_tiles; ++mt) {
-            if (epi_groups == 2 && ((c * p.m_tiles + mt) & 1) != epi_grp) continue;
+            if (epiB_groups == 2 && ((c * p.m_tiles + mt) & 1) != epi_grp) continue;   // the quarter's other warp takes it
             const int r = mt * 128 + q * 32 + lane;
             const int t = t0 + r;
             const bool ok = r < p.m_out && t < p.L;
@@ -1946,7 +1974,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             }
             uint32_t rr[16], r2[16];
             const uint32_t tcol = acc2 + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 2 * NT + c * 16);
+#if FV_AB_OLD_LD
+            tmem_ld16(tcol, rr);
+            tmem_ld16(tcol + (uint32_t)NT, r2);
+#else
             tmem_ld16x2(tcol, tcol + (uint32_t)NT, rr, r2);
+#endif
             if (!ok) continue;
             float v[16];
 #if FV_PACKED_F32
@@ -2048,7 +2081,9 @@ retry:
   // FV_TC3_PP: 0 = no ping-pong tiles, 1 = streamed-weight units only, 2 = also resident units with k >= 7 (default),
   // 3 = every resident unit
   static const int pp_env = getenv("FV_TC3_PP") ? atoi(getenv("FV_TC3_PP")) : 2;
-  if (best_sc >= 0 && (pp_env >= 3 || (pp_env == 2 && K >= 7))) {
+  // split (TMA-fed) units at C = 16: ping-pong tiles also for k = 3 (m 3 -> 8: eight independent accumulator chains per
+  // tile keep the tensor pipe fed, profiles/r02_notes.md: 311 -> 276 kclk); C = 32 k = 3 measured neutral (294 vs 297)
+  if (best_sc >= 0 && (pp_env >= 3 || (pp_env == 2 && (K >= 7 || (split && C <= 16))))) {
     // Resident weights + ping-pong tiles: the same two tiles in flight need half the TMEM and no A2 buffer, so the tile can be
     // taller (C=32: m 2 -> 4, C=16: m 3-4 -> 8): less conv2 halo recompute and fewer per-tile hand-offs.  Measured in one call
     // (gpurun_out/pp2_*): C=32 k=11 0.676 -> 0.60 ms, C=16 k=11 0.61 -> 0.52, k=7 -3 %, k=3 +-3 % (left on the old plans);
@@ -2113,8 +2148,8 @@ retry:
   p.pp = best_pp;
   p.w_stages = best_wst;
   p.stage_bytes = (int)stage_bytes;
-  // ring mode: warp 11 is the weight producer; split mode: warp 11 is the TMA producer once the images are resident
-  p.n_issuers = std::min(best_m, (best_res && !split) ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);
+  // ring mode: warp 11 is the weight producer
+  p.n_issuers = std::min(best_m, best_res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1);
   static const int force_iss = getenv("FV_TC3_ISSUERS") ? atoi(getenv("FV_TC3_ISSUERS")) : 0;   // tuning knob
   if (force_iss > 0) p.n_issuers = std::max(1, std::min(p.n_issuers, force_iss));
   p.acc_cols = best_m * 2 * C;
@@ -2157,7 +2192,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
   p.xs = x; p.ys = y;
   p.inv_slope = slope > 0.f ? 1.0f / slope : 1.0f;
   static const int epi_env = getenv("FV_TC3_EPI") ? atoi(getenv("FV_TC3_EPI")) : 2;   // epilogue warp groups in split mode
-  p.epi_groups = (io != IO_F32 && epi_env >= 2 && p.w_resident) ? 2 : 1;
+  p.epi_groups = (io != IO_F32 && epi_env >= 2) ? 2 : 1;
   p.w1img = l1.image; p.w2img = l2.image;
   p.slope = slope; p.acc_mode = acc_mode; p.acc_div = acc_div;
   CUtensorMap tm_main, tm_tail;

@@ -231,11 +231,17 @@ class _NativeGenerator(torch.nn.Module):
             self._bound_key = key
 
     def _get_workspace(self, B, T):
+        """One workspace per CUDA stream: two streams driving the same model never share activation buffers."""
         need = C.c_size_t()
         _lib.check(_lib.lib().fv_workspace_bytes(self._handle, B, T, C.byref(need)), "fv_workspace_bytes")
-        ws = self._workspace
-        if ws is None or ws.numel() < need.value or ws.device != self.device:
-            self._workspace = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
+        if self._workspace is None:
+            self._workspace = {}
+        key = (self.device, torch.cuda.current_stream(self.device).cuda_stream)
+        ws = self._workspace.get(key)
+        if ws is None or ws.numel() < need.value:
+            if len(self._workspace) >= 8:                 # bounded: drop the oldest stream's buffer
+                self._workspace.pop(next(iter(self._workspace)))
+            self._workspace[key] = ws = torch.empty(int(need.value), dtype=torch.uint8, device=self.device)
         return ws
 
     def out_length(self, T: int, flags: int = 0) -> int:

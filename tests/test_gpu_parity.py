@@ -640,9 +640,11 @@ def test_planner_knobs_keep_parity(knob):
     import subprocess
     import sys
     env = dict(os.environ, **knob)
+    sel = "(test_model_forward_matches_reference and hifigan-l)"
+    if not ({"FV_TC3_RING", "FV_NO_FUSE", "FV_SPLIT"} & set(knob)):   # those knobs turn (part of) the fused-unit kernel off: the
+        sel += " or test_fused_resblock1_unit_kernel"                # unit-level entry point then refuses the shape (by design)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REPO, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
-                          "-k", "(test_model_forward_matches_reference and hifigan-l) or test_fused_resblock1_unit_kernel"],
-                         capture_output=True, text=True, cwd=REPO, env=env, timeout=900)
+                          "-k", sel], capture_output=True, text=True, cwd=REPO, env=env, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
 
 
