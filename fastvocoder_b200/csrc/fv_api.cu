@@ -104,6 +104,10 @@ struct LayerCall {
   // (fv_tma.cuh) instead of fp32.  Tensor-core kernel only: run_layer returns FV_NOT_APPLICABLE when it cannot.
   bool out_split = false;
   float out_slope = 0.f;
+  // Conv1d on the tensor-core kernel: x (and res) are split-format buffers; x is fetched by TMA (pre_slope must be the slope
+  // baked into the copy), the residual is rebuilt from its copy (res_slope = the slope baked into it).
+  bool in_split = false, res_split = false;
+  float res_slope = 0.f;
 };
 constexpr int FV_NOT_APPLICABLE = 1;   // positive: not an error, the caller takes its fallback
 
@@ -178,10 +182,15 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   // HBM-bound k = 7 single-channel output convs (conv_post 16->1, LastLayer 32->1): the streaming kernel on both paths
   // (measured 0.305 -> 0.148 ms / 0.457 -> 0.265 ms = 3.5-3.8 TB/s).  The 64->4 conv_post of Multiband-HiFi-GAN is FMA-bound
   // there (0.56 ms) and stays on tcgen05 (0.47 ms) when tensor cores are allowed.
-  if (c.out_split) {
-    if (a.out_layout != OUT_PHASE || !c.allow_tc || tc_disabled || !tcl || !tcl->eligible || c.lens) return FV_NOT_APPLICABLE;
-    a.out_layout = OUT_PHASE_SPLIT;
+  if (c.out_split || c.in_split || c.res_split) {
+    if (!c.allow_tc || tc_disabled || !tcl || !tcl->eligible || c.lens) return FV_NOT_APPLICABLE;
+    if (a.out_layout != OUT_PHASE && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
+    if ((c.in_split || c.res_split) && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
+    if (c.out_split) a.out_layout = a.out_layout == OUT_PHASE ? OUT_PHASE_SPLIT : OUT_BCL_SPLIT;
     a.out_slope = c.out_slope;
+    a.x_split = c.in_split ? 1 : 0;
+    a.res_split = c.res_split ? 1 : 0;
+    a.res_inv_slope = (c.res_split && c.res_slope > 0.f) ? 1.0f / c.res_slope : 0.f;
     int rc = launch_conv_tc2(a, *tcl, st);
     if (rc < 0) return fail(FV_ECUDA, "tcgen05 conv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc == 0 && used_tc) *used_tc = 1;
@@ -202,6 +211,21 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   }
   FV_CUDA(launch_conv_ffma(a, st));
   return FV_OK;
+}
+
+// Would conv_tc2 take this ResBlock conv on the split / TMA activation chain?  (same ConvArgs run_layer builds)
+static bool tc2_split_ok(const Layer& l, const TcLayer* t, int nb, long long L, bool with_res, bool out_split) {
+  if (!t || !t->eligible || l.type != L_CONV) return false;
+  ConvArgs a{};
+  a.B = nb; a.Cin = l.Cin; a.N = l.N; a.Lin = (int)L; a.Lpos = (int)L; a.K = l.Kd; a.dil = l.dil;
+  a.pad_mode = PAD_ZERO; a.pad_left = (l.K - 1) * l.dil / 2; a.pre_slope = 0.1f;
+  a.out_layout = out_split ? OUT_BCL_SPLIT : OUT_BCL; a.out_slope = 0.1f; a.bias_mod = l.Cout;
+  a.x_split = 1; a.x_bs = (long long)l.Cin * L; a.y_bs = a.res_bs = (long long)l.Cout * L;
+  a.res = with_res ? reinterpret_cast<const float*>(0x10) : nullptr;   // only tested for null-ness by the planner
+  a.res_split = with_res ? 1 : 0; a.res_inv_slope = 10.f;
+  a.acc_mode = ACC_STORE;
+  Tc2Args p{};
+  return tc2_plan(a, *t, p, 148);
 }
 
 // ---- whole-model forward ----------------------------------------------------------------------------
@@ -377,6 +401,10 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       // split path: all units of the stage are fused ResBlock1 units that the planner accepts in split mode
       bool split_stage = m.is_hifi() && tc_ok && fuse_ok && split_env && !lens_dev && tc3_split_available() &&
                          !sg.branches.empty() && Lout < (1LL << 30);
+      // split_wide: the stage is too wide for the fused-unit kernel (C = 128 ...): the same split / TMA activation chain
+      // through conv_tc2 — conv1 (split in -> split h), conv2 (split h in, residual from the split x, split or fp32 out)
+      static const bool split_wide_env = getenv("FV_SPLIT_WIDE") == nullptr || atoi(getenv("FV_SPLIT_WIDE")) != 0;
+      bool split_wide = false;
       for (size_t j = 0; split_stage && j < sg.branches.size(); ++j)
         for (const ResUnit& ru : sg.branches[j].units) {
           Tc3Args probe{};
@@ -385,6 +413,22 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
           if (ru.c2 < 0 || !t1 || !t2 || !t1->eligible || !t2->eligible || t1->n_tiles != 1 || t2->n_tiles != 1 ||
               !tc3_plan(nb, la.Cin, (int)Lout, la.K, la.dil, probe, true)) { split_stage = false; break; }
         }
+      if (!split_stage && m.is_hifi() && tc_ok && split_env && split_wide_env && !lens_dev && tc3_split_available() &&
+          !sg.branches.empty() && Lout < (1LL << 30) && sg.Cout % 16 == 0) {
+        split_wide = true;
+        for (size_t j = 0; split_wide && j < sg.branches.size(); ++j)
+          for (const ResUnit& ru : sg.branches[j].units) {
+            const TcLayer *t1 = tcl(ru.c1), *t2 = ru.c2 >= 0 ? tcl(ru.c2) : nullptr;
+            if (ru.c2 < 0 || !t1 || !t2 || t1->n_pad != sg.Cout || t2->n_pad != sg.Cout ||
+                !tc2_split_ok(m.layers[ru.c1], t1, nb, Lout, false, true) ||
+                !tc2_split_ok(m.layers[ru.c2], t2, nb, Lout, true, true) ||
+                !tc2_split_ok(m.layers[ru.c2], t2, nb, Lout, true, false)) {
+              split_wide = false;
+              break;
+            }
+          }
+        split_stage = split_wide;   // the upsample layer writes the split copy either way
+      }
       {  // LeakyReLU + ConvTranspose1d
         LayerCall lc;
         lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L; lc.lens = lens_at((int)s - 1, b0);
@@ -416,8 +460,26 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
             if (last && mrf_red && nb_br > 1) {   // 1/num_kernels folded into every branch, no read of the running sum
               acc = (j == 0) ? ACC_STORE_SCALE : ACC_RED_SCALE; div = (float)nb_br;
             } else if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
+            if (br.units[u].c2 >= 0 && split_wide) {   // unfused unit on the split / TMA chain (conv_tc2 x 2)
+              LayerCall l1;
+              l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
+              l1.in_split = true; l1.out_split = true; l1.out_slope = 0.1f;
+              rc = call(br.units[u].c1, l1);
+              if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "split-chain conv1 was not applicable after planning");
+              if (rc) return rc;
+              LayerCall l2;
+              l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.1f;
+              l2.in_split = true; l2.res_split = true; l2.res_slope = 0.1f;
+              l2.out_split = !last; l2.out_slope = 0.1f;
+              l2.acc_mode = acc; l2.acc_div = div;
+              rc = call(br.units[u].c2, l2);
+              if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "split-chain conv2 was not applicable after planning");
+              if (rc) return rc;
+              bc = dst;
+              continue;
+            }
             if (br.units[u].c2 >= 0) {  // ResBlock1 unit (modules.py:224-229)
-              if (tc_ok && fuse_ok) {   // one kernel: conv1 -> lrelu -> conv2 -> +x, h stays in shared memory
+              if (tc_ok && fuse_ok && !split_wide) {   // one kernel: conv1 -> lrelu -> conv2 -> +x, h stays in shared memory
                 const Layer& la = m.layers[br.units[u].c1];
                 const TcLayer* t1 = tcl(br.units[u].c1);
                 const TcLayer* t2 = tcl(br.units[u].c2);

@@ -24,7 +24,9 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 }
 // OUT_PHASE_SPLIT (tensor-core kernel only): the polyphase ConvTranspose output, LeakyReLU(out_slope)-activated and split
 // into fp16 hi / lo in the blocked "split" activation format the fused ResBlock units fetch by TMA (fv_tma.cuh).
-enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2, OUT_PHASE_SPLIT = 3 };
+// OUT_BCL_SPLIT: the same for a stride-1 conv output [B, N, L] (h of an unfused ResBlock unit / the unit output that the
+// next unit consumes).
+enum { OUT_BCL = 0, OUT_BLC = 1, OUT_PHASE = 2, OUT_PHASE_SPLIT = 3, OUT_BCL_SPLIT = 4 };
 
 struct ConvArgs {
   const float* x;     // [B, Cin, Lin]
@@ -42,7 +44,12 @@ struct ConvArgs {
   int bias_mod;
   // OUT_PHASE (ConvTranspose1d): n = r*ph_cout + co ; t = pos*ph_stride + r - ph_pad in [0, ph_lout)
   int ph_stride, ph_pad, ph_cout, ph_lout;
-  float out_slope;               // OUT_PHASE_SPLIT: LeakyReLU slope baked into the split copy (the consumers' pre-activation)
+  float out_slope;               // OUT_*_SPLIT: LeakyReLU slope baked into the split copy (the consumers' pre-activation)
+  // tensor-core kernel only: x / res are split-format buffers (fv_tma.cuh) instead of fp32 [B, C, L].  x_split: the A
+  // tiles are fetched by TMA (zero padding only; the copy is already activated with pre_slope); res_split: the residual
+  // is rebuilt from the split copy, whose baked slope is 1 / res_inv_slope.
+  int x_split, res_split;
+  float res_inv_slope;
   long long x_bs, y_bs, res_bs;  // batch strides in floats
   // two-input form (L_PAIR): input channels >= cin_split come from x2 (own pre-activation); 0 = single input
   const float* x2;

@@ -271,6 +271,20 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi2, u
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(l1), "f"(l0));
 }
 
+// hi / lo rows (8 channels each) of the split copy -> the un-activated fp32 values: v = hi + lo (exact in fp32),
+// x = min(v, v / slope) undoes LeakyReLU for 0 < slope <= 1.
+__device__ __forceinline__ void unsplit8(const uint4& h, const uint4& l, float inv_slope, float* out) {
+  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
+    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ll[j]));
+    const float v0 = fh.x + fl.x, v1 = fh.y + fl.y;
+    out[2 * j] = fminf(v0, v0 * inv_slope);
+    out[2 * j + 1] = fminf(v1, v1 * inv_slope);
+  }
+}
+
 // Flattened fill of one A stage.  The (8-channel group kc, row r) items of the stage are dealt round-robin over the
 // 256 loader threads: item i = kc * rows + r, thread ltid takes i = ltid + 256 t.  Every thread then has `per` items =
 // 8 * per independent global loads in flight per round, and a stage whose row count is not a multiple of 128 (every
@@ -554,6 +568,8 @@ struct Tc2Args {
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
   int ck, nck;       // K-chunking: an A stage holds `ck` input channels of the tile; nck = Cin / ck stages per tile
+  int rows_alloc;    // row stride of the A planes (= rows; rounded up to 8 with a split / TMA-fed input: 128-B aligned boxes)
+  int epi_groups;    // split input: warps 4-7 are a second epilogue group (no loader warps then)
   int cluster_mode;  // experimental (FV_CLUSTER): 1 = pairs, private weight copies; 2 = each CTA multicasts its half; 3 = rank 0 multicasts all
   int n_issuers;     // UMMA issuer warps in use (1..4; at most 3 when the weight ring needs warp 11)
   int dual;          // 1: B = [B_hi | B_lo] as one N = 2*NT operand (2 UMMAs / k-block), 0: three N = NT UMMAs
@@ -573,7 +589,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // tcgen05.ld -> + bias -> [tanh] -> coalesced stores (ConvTranspose: phase interleave; narrow layers: masked tail columns).
 template <int LAYOUT, bool DBG>
 __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                  int nt, WaitAcc<DBG>& wa) {
+                                                  int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const int nchunks = p.NT >> 4;
@@ -595,6 +611,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
       for (int i = 0; i < 16; ++i) bias[i] = 0.f;
     }
     for (int mt = 0; mt < p.m_tiles; ++mt) {
+      if (ngrp == 2 && ((c * p.m_tiles + mt) & 1) != grp) continue;   // the lane quarter's other epilogue warp takes it
       const int pos = t0 + mt * 128 + q * 32 + lane;
       uint32_t rr[16];
       const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
@@ -610,7 +627,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
       if (DBG) { const long long t1 = clock64(); wa.w[1] += t1 - tdbg; tdbg = t1; }   // "tmem": TMEM read + wait::ld
       int o0, ostride;   // 32-bit offsets inside the utterance's output plane (tc2_plan rejects planes >= 2^31 elements)
       bool ok = pos < a.Lpos;
-      if (LAYOUT == OUT_BCL) {
+      if (LAYOUT == OUT_BCL || LAYOUT == OUT_BCL_SPLIT) {
         o0 = nbase * a.Lpos + pos; ostride = a.Lpos;
       } else if (LAYOUT == OUT_BLC) {
         o0 = pos * a.N + nbase; ostride = 1;
@@ -620,6 +637,21 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
         o0 = co0 * a.ph_lout + t; ostride = a.ph_lout;
       }
       if (!ok) continue;
+      if (LAYOUT == OUT_BCL_SPLIT) {   // h of an unfused ResBlock unit: lrelu -> fp16 hi / lo rows of the blocked planes [2][N/8][Lpos]
+        uint32_t hp[8], lp[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          split_f16x2(lrelu01(__uint_as_float(rr[i]) + bias[i], a.out_slope),
+                      lrelu01(__uint_as_float(rr[i + 1]) + bias[i + 1], a.out_slope), hp[i >> 1], lp[i >> 1]);
+        const uint32_t ul = (uint32_t)a.Lpos, lo_off = (uint32_t)(a.N >> 3) * ul;
+        uint4* yq = opaque_ptr(reinterpret_cast<uint4*>(yb) + ((uint32_t)(nbase >> 3) * ul + (uint32_t)pos));
+        yq[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        yq[ul] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        yq[lo_off] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        yq[lo_off + ul] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+        if (DBG) wa.w[4] += clock64() - tdbg;
+        continue;
+      }
       if (LAYOUT == OUT_PHASE_SPLIT) {
         // split copy for the TMA-fed fused units: lrelu(out_slope) -> fp16 hi / lo -> rows of 16 B in the blocked planes
         // uint4 [2 (hi, lo)][Cout/8][Lout]; a 16-column chunk covers planes co0/8 and co0/8 + 1 of both halves
@@ -666,9 +698,11 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
 // Epilogue for [B, C, L] layers WITH an addend from global memory: y = conv + bias + residual [+ running MRF sum,
 // / num_kernels].  The addend does not depend on the accumulators, so its loads are issued before the TMEM read:
 // one memory latency per (chunk, M tile) instead of two or three back to back.  (No padded-N layers here: run_layer.)
-template <bool DBG>
+// RS: the residual is a split-format copy (4 x 16-byte loads per 16 channels, rebuilt with unsplit8);
+// OS: the output is written LeakyReLU(out_slope)-activated in the split format (the next unit's TMA-fed input).
+template <bool DBG, bool RS, bool OS>
 __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                      int nt, WaitAcc<DBG>& wa) {
+                                                      int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
@@ -679,19 +713,31 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
   const bool red = a.acc_mode == ACC_RED_SCALE;
   const int ostride = a.Lpos;   // 32-bit offsets inside the utterance plane (tc2_plan)
   const uint32_t uos = (uint32_t)ostride;
+  const uint32_t q_lo = (uint32_t)(a.N >> 3) * uos;   // split planes: lo half starts N/8 planes after the hi half
   const int row = q * 32 + lane;
-  // The residual of iteration it+1 is requested before iteration it is processed (software pipelining: two sets of
-  // loads in flight per warp instead of one; these four warps are latency-bound, not bandwidth-bound).
-  float nxt[16];
-  {
-    const bool ok0 = t0 + row < a.Lpos;
-    const int o = (nt * p.NT) * a.Lpos + t0 + row;
-    const float* pr = opaque_ptr(rb + ((rb && ok0) ? o : 0));
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  // The residual of this group's NEXT iteration is requested before the current one is processed (software pipelining:
+  // two sets of loads in flight per warp; these warps are latency-bound, not bandwidth-bound).
+  float nxt[RS ? 1 : 16];
+  uint4 nq[RS ? 4 : 1];
+  auto fetch = [&](int it2) {
+    const int c2 = it2 / p.m_tiles, mt2 = it2 - c2 * p.m_tiles;
+    const int pos2 = t0 + mt2 * 128 + row;
+    const bool ok2 = rb != nullptr && pos2 < a.Lpos;
+    const int nb2 = nt * p.NT + c2 * 16;
+    if (RS) {
+      const uint4* pr = opaque_ptr(reinterpret_cast<const uint4*>(rb) + (ok2 ? (uint32_t)(nb2 >> 3) * uos + (uint32_t)pos2 : 0u));
+      nq[0] = ok2 ? __ldg(pr) : z4; nq[1] = ok2 ? __ldg(pr + uos) : z4;
+      nq[2] = ok2 ? __ldg(pr + q_lo) : z4; nq[3] = ok2 ? __ldg(pr + q_lo + uos) : z4;
+    } else {
+      const float* pr = opaque_ptr(rb + (ok2 ? nb2 * a.Lpos + pos2 : 0));
 #pragma unroll
-    for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok0) ? __ldg(pr + (uint32_t)i * uos) : 0.f;
-  }
-  int c = 0, mt = 0;
-  for (int it = 0; it < n_it; ++it) {
+      for (int i = 0; i < 16; ++i) nxt[i] = ok2 ? __ldg(pr + (uint32_t)i * uos) : 0.f;
+    }
+  };
+  if (grp < n_it) fetch(grp);
+  for (int it = grp; it < n_it; it += ngrp) {
+    const int c = it / p.m_tiles, mt = it - c * p.m_tiles;
     const int nbase = nt * p.NT + c * 16;
     const int pos = t0 + mt * 128 + row;
     const bool ok = pos < a.Lpos;
@@ -699,20 +745,16 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
     float addend[16];
     long long tld = 0;
     if (DBG) tld = clock64();
+    if (RS) {
+      unsplit8(nq[0], nq[2], a.res_inv_slope, addend);
+      unsplit8(nq[1], nq[3], a.res_inv_slope, addend + 8);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) addend[i] = nxt[i];
-    int c2 = c, mt2 = mt + 1;
-    if (mt2 == p.m_tiles) { mt2 = 0; ++c2; }
-    if (it + 1 < n_it) {
-      const int pos2 = t0 + mt2 * 128 + row;
-      const bool ok2 = pos2 < a.Lpos;
-      const int o2 = (nt * p.NT + c2 * 16) * a.Lpos + pos2;
-      const float* pr = opaque_ptr(rb + ((rb && ok2) ? o2 : 0));
-#pragma unroll
-      for (int i = 0; i < 16; ++i) nxt[i] = (rb && ok2) ? __ldg(pr + (uint32_t)i * uos) : 0.f;
+      for (int i = 0; i < 16; ++i) addend[i] = nxt[i];
     }
+    if (it + ngrp < n_it) fetch(it + ngrp);
     float* py = opaque_ptr(yb + (ok ? o0 : 0));
-    if (acc_reads_y(a.acc_mode)) {
+    if (!OS && acc_reads_y(a.acc_mode)) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) addend[i] += ok ? py[(uint32_t)i * uos] : 0.f;
     }
@@ -720,12 +762,13 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
     const uint32_t tcol = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NT * (p.dual ? 2 : 1) + c * 16);
     long long tdbg = 0;
     if (DBG) { tdbg = clock64(); wa.w[3] += tdbg - tld; }   // "ldissue": issuing the residual / running-sum loads
-    tmem_ld16(tcol, rr);
     if (p.dual) {
       uint32_t r2[16];
-      tmem_ld16(tcol + (uint32_t)p.NT, r2);
+      tmem_ld16x2(tcol, tcol + (uint32_t)p.NT, rr, r2);
 #pragma unroll
       for (int i = 0; i < 16; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + __uint_as_float(r2[i]));
+    } else {
+      tmem_ld16(tcol, rr);
     }
     if (DBG) {
       const long long t1 = clock64();
@@ -746,7 +789,18 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
           addend[4 * i4] += bv.x; addend[4 * i4 + 1] += bv.y; addend[4 * i4 + 2] += bv.z; addend[4 * i4 + 3] += bv.w;
         }
       }
-      if (red) {
+      if (OS) {
+        uint32_t hp[8], lp[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          split_f16x2(lrelu01(__uint_as_float(rr[i]) + addend[i], a.out_slope),
+                      lrelu01(__uint_as_float(rr[i + 1]) + addend[i + 1], a.out_slope), hp[i >> 1], lp[i >> 1]);
+        uint4* yq = opaque_ptr(reinterpret_cast<uint4*>(yb) + ((uint32_t)(nbase >> 3) * uos + (uint32_t)pos));
+        yq[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        yq[uos] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        yq[q_lo] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        yq[q_lo + uos] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+      } else if (red) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) red_add_f32(py + (uint32_t)i * uos, (__uint_as_float(rr[i]) + addend[i]) * inv);
       } else {
@@ -755,17 +809,19 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
       }
     }
     if (DBG) wa.w[4] += clock64() - tdbg;        // "store": bias add + issuing the 16 stores
-    c = c2; mt = mt2;
   }
 }
 
-template <bool DBG>
-__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args p) {
+// XS: the input is a split-format buffer (fv_tma.cuh) fetched by TMA — no loader warps: warp 0 is the TMA producer and
+// warps 4-7 a second epilogue group.
+template <bool DBG, bool XS>
+__global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args p, const __grid_constant__ CUtensorMap tm_main,
+                                                                  const __grid_constant__ CUtensorMap tm_tail) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
   const ConvArgs& a = p.a;
   const int rows = p.rows;
-  const uint32_t a_bytes = (uint32_t)rows * p.ck * 2;   // hi or lo of one A stage (one channel chunk of the tile)
+  const uint32_t a_bytes = (uint32_t)p.rows_alloc * p.ck * 2;   // hi or lo of one A stage (one channel chunk of the tile)
   const int kblock_bytes = p.NT * 64;
   const int kpc = p.ck >> 4;                              // 16-channel k-steps per chunk
   const int runs_per_grp = (kpc + p.kb_per_stage - 1) / p.kb_per_stage;   // ring stages per (chunk, tap)
@@ -792,12 +848,13 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   const int cl_base = (int)blockIdx.x - (int)cr;                      // lowest blockIdx.x of my cluster
   const int ring_tiles = (p.total_tiles > cl_base) ? (p.total_tiles - cl_base + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+  const int epi_groups = (XS && p.epi_groups == 2) ? 2 : 1;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(0 + s), TC2_LOADER_WARPS);   // a_full: one arrive per loader warp
+      mbar_init(BAR(0 + s), XS ? 1 : TC2_LOADER_WARPS);   // a_full: one arrive per loader warp / one expect_tx + the TMA bytes
       mbar_init(BAR(2 + s), p.n_issuers);   // a_empty: one tcgen05.commit per issuer
       mbar_init(BAR(4 + s), p.n_issuers);   // acc_full: one tcgen05.commit per issuer
-      mbar_init(BAR(6 + s), 4);   // acc_empty: one arrive per epilogue warp
+      mbar_init(BAR(6 + s), 4 * epi_groups);   // acc_empty: one arrive per epilogue warp
     }
     for (int s = 0; s < 8; ++s) {
       mbar_init(BAR(8 + s), 1);                // w_full: expect_tx by the producer
@@ -813,7 +870,40 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < TC2_LOADER_WARPS) {
+  const bool is_epi = warp >= TC2_LOADER_WARPS + TC2_ISSUE_WARPS || (epi_groups == 2 && warp >= 4 && warp < TC2_LOADER_WARPS);
+  if (XS && warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: split planes -> A[stage]
+    const int nkc = p.ck >> 3, planes_b = a.Cin >> 3;
+    const int nfull = rows / TMA_SPLIT_RB, tail = rows - nfull * TMA_SPLIT_RB;
+    const int nrb = nfull + (tail ? 1 : 0);
+    const int per_half = nkc * nrb, nops = 2 * per_half;
+    const uint32_t stage_tx = (uint32_t)(2 * nkc * rows * 16);
+    if (lane == 0) { tma_prefetch_desc(&tm_main); tma_prefetch_desc(&tm_tail); }
+    int u = 0;
+    WaitAcc<DBG> wa;
+    wa.begin();
+    if (p.pdl) pdl_wait();
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_batch;
+      const int g0 = (tile - b * p.tiles_per_batch) * M - a.pad_left;
+      for (int ch = 0; ch < p.nck; ++ch, ++u) {
+        const int s = u % p.a_stages;
+        if (u >= p.a_stages) wa.wait(0, BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
+        if (lane == 0) mbar_expect_tx(BAR(0 + s), stage_tx);
+        __syncwarp();
+        const uint32_t a_hi = smem_u32(Abuf + (size_t)s * 2 * a_bytes);
+        for (int i = lane; i < nops; i += 32) {
+          const int half = i >= per_half ? 1 : 0;
+          const int rem = i - half * per_half;
+          const int kc = rem / nrb, rb = rem - kc * nrb;
+          const uint32_t dst = a_hi + (uint32_t)half * a_bytes + (uint32_t)(kc * p.rows_alloc + rb * TMA_SPLIT_RB) * 16u;
+          tma_load_2d(dst, rb < nfull ? &tm_main : &tm_tail, 2 * (g0 + rb * TMA_SPLIT_RB),
+                      (b * 2 + half) * planes_b + ch * nkc + kc, BAR(0 + s));
+        }
+      }
+    }
+    wa.end(p.dbg, 0, lane == 0, u);
+  } else if (!XS && warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders
     const int nkc = p.ck >> 3;                  // 8-channel groups per chunk
     const int nrb = (rows + 127) >> 7;          // row blocks of 128 (4 rows per lane)
@@ -898,7 +988,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       }
     }
     wa.end(p.dbg, 0, warp == 0 && lane == 0, u);
-  } else if (warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
+  } else if (warp >= TC2_LOADER_WARPS && warp < TC2_LOADER_WARPS + TC2_ISSUE_WARPS) {
     // ------------------------------------------------------------------ weight producer + UMMA issuers
     const int wid = warp - TC2_LOADER_WARPS;                 // 0..3
     const bool is_producer = (wid == TC2_ISSUE_WARPS - 1);
@@ -953,7 +1043,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       if (wid < p.n_issuers) {   // (in ring mode n_issuers <= 3, so the producer never gets here)
         WaitAcc<DBG> wa;
         wa.begin();
-        const uint32_t a_lbo = (uint32_t)rows * 16;
+        const uint32_t a_lbo = (uint32_t)p.rows_alloc * 16;
         const uint32_t b_lbo = (uint32_t)p.NT * 32;
         const uint32_t wbase = smem_u32(Wbuf);
         if (p.w_resident) wa.wait(0, BAR(8), 0, 600);
@@ -969,7 +1059,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         const bool dual = p.dual != 0, resident = p.w_resident != 0, reuse = p.a_reuse != 0;
         const uint32_t kb16 = (uint32_t)kblock_bytes >> 4;                  // one weight k-block, in 16-B units
         const uint64_t nt16 = (uint64_t)p.NT;
-        const uint64_t ks_step16 = 2ull * (uint64_t)rows;                   // next 16-channel k-step of the A stage
+        const uint64_t ks_step16 = 2ull * (uint64_t)p.rows_alloc;           // next 16-channel k-step of the A stage
         const int my_mts = (m_tiles - wid + n_iss - 1) / n_iss;             // M tiles wid, wid + n_iss, ... (<= 4, see tc2_plan)
         __syncwarp();                                                       // elect.sync needs the full warp converged
         int it = 0, g = 0, u = 0;
@@ -1057,9 +1147,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       }
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue warps (4 consecutive warps)
+  } else if (is_epi) {
+    // ------------------------------------------------------------------ epilogue warps (one or two per TMEM lane quarter)
     const int q = warp & 3;
+    const int grp = warp < TC2_LOADER_WARPS ? 1 : 0;
     int it = 0;
     WaitAcc<DBG> wa;
     wa.begin();
@@ -1071,16 +1162,20 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       const int b = tile / p.tiles_per_batch;
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
-      if (a.out_layout == OUT_BCL && (a.res != nullptr || a.acc_mode != ACC_STORE)) tc2_epilogue_tile_add<DBG>(p, acc, q, lane, b, t0, nt, wa);
-      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa);
-      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa);
-      else if (a.out_layout == OUT_PHASE_SPLIT) tc2_epilogue_tile<OUT_PHASE_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa);
-      else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa);
+      const bool has_add = a.res != nullptr || a.acc_mode != ACC_STORE;
+      if (a.out_layout == OUT_BCL_SPLIT && has_add) tc2_epilogue_tile_add<DBG, true, true>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_BCL_SPLIT) tc2_epilogue_tile<OUT_BCL_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_BCL && has_add && a.res_split) tc2_epilogue_tile_add<DBG, true, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_BCL && has_add) tc2_epilogue_tile_add<DBG, false, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else if (a.out_layout == OUT_PHASE_SPLIT) tc2_epilogue_tile<OUT_PHASE_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(6 + as));
     }
-    wa.end(p.dbg, 3, q == 0 && lane == 0, it);
+    wa.end(p.dbg, 3, q == 0 && lane == 0 && grp == 0, it);
   }
   tc_fence_before();
   __syncthreads();
@@ -1089,7 +1184,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 }
 
 inline size_t tc2_smem_bytes(const Tc2Args& p) {
-  const size_t a_bytes = (size_t)p.rows * p.ck * 2;
+  const size_t a_bytes = (size_t)p.rows_alloc * p.ck * 2;
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * p.NT * 64 : (size_t)p.w_stages * p.stage_bytes;
   return p.a_stages * 2 * a_bytes + w_bytes + 33 * 8;
 }
@@ -1105,7 +1200,18 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const long long w_total = (long long)kblocks * kblock_bytes;
   const long long BUDGET = 225 * 1024;
   static const int force_dual = getenv("FV_TC2_DUAL") ? atoi(getenv("FV_TC2_DUAL")) : -1;   // tuning knob: 0 / 1
-  if ((a.res != nullptr || a.acc_mode != ACC_STORE) && (a.out_layout != OUT_BCL || a.post_tanh)) return false;
+  static const int force_mt_xs = getenv("FV_TC2_MT_XS") ? atoi(getenv("FV_TC2_MT_XS")) : 0;   // tuning knob: M tiles per CTA tile, split-input layers
+  if ((a.res != nullptr || a.acc_mode != ACC_STORE) && ((a.out_layout != OUT_BCL && a.out_layout != OUT_BCL_SPLIT) || a.post_tanh)) return false;
+  if (a.out_layout == OUT_BCL_SPLIT &&
+      (a.acc_mode != ACC_STORE || a.N % 16 || L.n_pad != a.N || a.post_tanh || !(a.out_slope >= 0.f && a.out_slope <= 1.f) ||
+       (a.res != nullptr && !a.res_split)))
+    return false;
+  if (a.res_split && (a.res == nullptr || a.N % 16 || !(a.res_inv_slope >= 1.f))) return false;
+  // split (TMA-fed) input: zero padding only (OOB rows of the tensor map), single dense input, no ragged batch
+  if (a.x_split && (a.pad_mode != PAD_ZERO || a.cin_split != 0 || a.lens != nullptr || a.Cin % 16 ||
+                    a.x_bs != (long long)a.Cin * a.Lin || !tma_encode_fn()))
+    return false;
+  auto xr = [&](long long rows) { return a.x_split ? (rows + 7) / 8 * 8 : rows; };   // 128-byte aligned TMA boxes
   {  // the kernels index inside one utterance's input / output plane with 32-bit element offsets
     const long long lim = 0x7fffffffLL - 65536;
     const long long out_plane = (a.out_layout == OUT_PHASE || a.out_layout == OUT_PHASE_SPLIT) ? (long long)a.ph_cout * a.ph_lout
@@ -1158,11 +1264,12 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
         for (int a_st = 2; a_st >= 1; --a_st)
           for (int mt = 8; mt >= 1; --mt) {
             if (mt * NT * df > 512) continue;
+            if (force_mt_xs > 0 && a.x_split && phase == 1 && mt != std::min(force_mt_xs, std::min(need_mt, 512 / (NT * df)))) continue;
             if (mt > need_mt && mt > 1) continue;
             if (nck > 1 && a_st < 2) continue;    // chunking only pays with double-buffered stages
             for (int w_st = (res ? 1 : 8); w_st >= (res ? 1 : 2); --w_st) {
               const long long wb = res ? w_total : (long long)w_st * stage_bytes;
-              const long long a_stage = 2LL * (mt * 128 + halo) * ck * 2;
+              const long long a_stage = 2LL * xr(mt * 128 + halo) * ck * 2;
               if (a_st * a_stage + wb + 512 > BUDGET) continue;
               const bool acc2 = 2 * mt * NT * df <= 512;
               int ni = res ? TC2_ISSUE_WARPS : TC2_ISSUE_WARPS - 1;
@@ -1173,7 +1280,8 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
               const double t_mma = std::max((double)kblocks * mt * c_pipe, (double)kblocks * my_mts * n_umma * 20.0);
               const int rows_t = mt * 128 + halo;
               const int pairs = (ck / 8) * ((rows_t + 127) / 128);
-              const double t_load = nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
+              const double t_load = a.x_split ? nck * (double)rows_t * ck * 4.0 / 40.0   // TMA: bandwidth only, no loader rounds
+                                              : nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
               const double ring_bw = std::min(14.0, (double)wb / 2500.0);
               const double t_w = res ? 0.0 : (double)w_total / ring_bw;
               const double t_epi = (double)mt * 128 * NT *
@@ -1203,6 +1311,9 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   p.NT = NT;
   p.m_tiles = best.mt;
   p.rows = best.mt * 128 + halo;
+  p.rows_alloc = (int)xr(p.rows);
+  static const int epi2_env = getenv("FV_TC2_EPI") ? atoi(getenv("FV_TC2_EPI")) : 2;
+  p.epi_groups = (a.x_split && epi2_env >= 2) ? 2 : 1;
   p.ksteps = ksteps;
   p.kblocks = kblocks;
   p.a_stages = best.a_st;
@@ -1319,8 +1430,11 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
       num_sms[dev] = prop.multiProcessorCount;
     }
     if (!attr_set[dev]) {
-      if (cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      const int mx = 227 * 1024;
+      if (cudaFuncSetAttribute(conv_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
         return -1;
       attr_set[dev] = true;
     }
@@ -1329,12 +1443,25 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   if (!L.eligible || !L.image || !tc2_plan(a, L, p, num_sms[dev])) return 1;
   p.wimg = L.image;
   const size_t smem = tc2_smem_bytes(p);
+  CUtensorMap tm_main, tm_tail;
+  memset(&tm_main, 0, sizeof tm_main);
+  memset(&tm_tail, 0, sizeof tm_tail);
+  if (a.x_split) {
+    const long long planes = (long long)a.B * 2 * (a.Cin / 8);
+    const int tail = p.rows % TMA_SPLIT_RB;
+    if (!tma_encode_split(&tm_main, a.x, a.Lin, planes, TMA_SPLIT_RB)) return 1;
+    if (tail) {
+      if (!tma_encode_split(&tm_tail, a.x, a.Lin, planes, tail)) return 1;
+    } else {
+      tm_tail = tm_main;
+    }
+  }
   int gx = num_sms[dev] / L.n_tiles;
   if (gx < 1) gx = 1;
   if (gx > p.total_tiles) gx = p.total_tiles;
   // EXPERIMENTAL (round 1): the multicast ring produces wrong results on hardware, so it is opt-in until debugged.
   static const int cluster_mode = getenv("FV_CLUSTER") ? atoi(getenv("FV_CLUSTER")) : 0;
-  const int cs = (!p.w_resident && cluster_mode > 0 && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
+  const int cs = (!p.w_resident && cluster_mode > 0 && !a.x_split && num_sms[dev] / L.n_tiles >= 2) ? 2 : 1;
   p.cluster_mode = cs == 2 ? cluster_mode : 0;
   if (cs == 2) gx = (gx + 1) & ~1;   // pairs; an odd tile count leaves one CTA with ring duty only
   if (cs == 2 && gx > num_sms[dev] / L.n_tiles) gx -= 2;
@@ -1362,7 +1489,8 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
     StallReport rep;
     if (!rep.begin(gx * L.n_tiles)) return -1;
     p.dbg = rep.dev;
-    le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, p);
+    le = a.x_split ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, true>, p, tm_main, tm_tail)
+                   : cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true, false>, p, tm_main, tm_tail);
     static const char* const roles[8] = {"loader", "producer", "issuer0", "epilogue", nullptr, nullptr, nullptr, nullptr};
     static const char* const slots[8][5] = {{"a_empty", nullptr, nullptr, nullptr, nullptr},
                                             {"w_empty", "w_free", nullptr, nullptr, nullptr},
@@ -1377,7 +1505,8 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
              L.n_tiles);
     rep.finish(st, title, roles, slots);
   } else {
-    le = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false>, p);
+    le = a.x_split ? cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, true>, p, tm_main, tm_tail)
+                   : cudaLaunchKernelEx(&cfg, conv_tc2_kernel<false, false>, p, tm_main, tm_tail);
   }
   g_launches++;
   g_tc_launches++;
@@ -1462,20 +1591,6 @@ __device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_
 }
 
 enum { IO_F32 = 0, IO_SPLIT_SPLIT = 1, IO_SPLIT_F32 = 2 };
-
-// hi / lo rows (8 channels each) of the split copy -> the un-activated fp32 values: v = hi + lo (exact in fp32),
-// x = min(v, v / slope) undoes LeakyReLU for 0 < slope <= 1.
-__device__ __forceinline__ void unsplit8(const uint4& h, const uint4& l, float inv_slope, float* out) {
-  const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hh[j]));
-    const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ll[j]));
-    const float v0 = fh.x + fl.x, v1 = fh.y + fl.y;
-    out[2 * j] = fminf(v0, v0 * inv_slope);
-    out[2 * j + 1] = fminf(v1, v1 * inv_slope);
-  }
-}
 
 template <bool DBG, int IO>
 __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p, const __grid_constant__ CUtensorMap tm_main,
