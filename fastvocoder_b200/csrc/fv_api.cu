@@ -108,6 +108,7 @@ struct LayerCall {
   // baked into the copy), the residual is rebuilt from its copy (res_slope = the slope baked into it).
   bool in_split = false, res_split = false;
   float res_slope = 0.f;
+  const float* ysum = nullptr;   // split output of the last MRF branch: fp32 running sum of the other branches
 };
 constexpr int FV_NOT_APPLICABLE = 1;   // positive: not an error, the caller takes its fallback
 
@@ -185,8 +186,9 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   if (c.out_split || c.in_split || c.res_split) {
     if (!c.allow_tc || tc_disabled || !tcl || !tcl->eligible || c.lens) return FV_NOT_APPLICABLE;
     if (a.out_layout != OUT_PHASE && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
-    if ((c.in_split || c.res_split) && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
+    if (c.res_split && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
     if (c.out_split) a.out_layout = a.out_layout == OUT_PHASE ? OUT_PHASE_SPLIT : OUT_BCL_SPLIT;
+    a.ysum = c.ysum;
     a.out_slope = c.out_slope;
     a.x_split = c.in_split ? 1 : 0;
     a.res_split = c.res_split ? 1 : 0;
@@ -226,6 +228,23 @@ static bool tc2_split_ok(const Layer& l, const TcLayer* t, int nb, long long L, 
   a.acc_mode = ACC_STORE;
   Tc2Args p{};
   return tc2_plan(a, *t, p, 148);
+}
+
+// Would conv_tc2 take this upsample layer (ConvTranspose1d / UpsampleLayer, polyphase) with a split / TMA-fed input?
+static bool tc2_up_split_in_ok(const Layer& l, const TcLayer* t, int nb, long long Lin, bool out_split) {
+  if (!t || !t->eligible || (l.type != L_CONVT && l.type != L_UPCONV)) return false;
+  ConvArgs a{};
+  const long long Lout = Model::convt_out_len(l, Lin);
+  a.B = nb; a.Cin = l.Cin; a.N = l.N; a.Lin = (int)Lin; a.K = l.Kd; a.dil = l.dil;
+  a.Lpos = l.type == L_CONVT ? (int)((Lout - 1 + l.padding) / l.stride + 1) : (int)((Lout + l.stride - 1) / l.stride);
+  a.pad_left = l.type == L_CONVT ? l.Kd - 1 : -l.dmin;
+  a.pad_mode = PAD_ZERO; a.pre_slope = 0.1f;
+  a.out_layout = out_split ? OUT_PHASE_SPLIT : OUT_PHASE; a.out_slope = 0.1f; a.bias_mod = l.Cout;
+  a.ph_stride = l.stride; a.ph_pad = l.type == L_CONVT ? l.padding : 0; a.ph_cout = l.Cout; a.ph_lout = (int)Lout;
+  a.x_split = 1; a.x_bs = (long long)l.Cin * Lin; a.y_bs = a.res_bs = (long long)l.Cout * Lout;
+  a.acc_mode = ACC_STORE;
+  Tc2Args p{};
+  return a.pad_left >= 0 && tc2_plan(a, *t, p, 148);
 }
 
 // ---- whole-model forward ----------------------------------------------------------------------------
@@ -372,11 +391,27 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   long long L = T;
   float* cur = bufA;
   float* other = bufB;
+  // Split (TMA-native) activation chain across stages: `cur_split` = the stage input in `cur` is a split copy with LeakyReLU 0.1
+  // baked in (written by conv_pre / by the last MRF branch of the previous stage) and the upsample layer fetches it by TMA.
+  static const bool split_env0 = getenv("FV_SPLIT") == nullptr || atoi(getenv("FV_SPLIT")) != 0;
+  static const bool split_final_env = getenv("FV_SPLIT_FINAL") == nullptr || atoi(getenv("FV_SPLIT_FINAL")) != 0;
+  const bool chain_ok = m.is_hifi() && tc_ok && split_env0 && split_final_env && !lens_host && tc3_split_available() &&
+                        !m.stages.empty();
+  bool cur_split = false;
   {  // conv_pre (hifigan.py:93, zero pad) / ReflectionPad1d + Conv1d (melgan.py:68-71)
     LayerCall lc;
     lc.x = x_in; lc.y = cur; lc.B = Be; lc.Lin = L; lc.lens = lens_at(-1, 0);
     lc.pad_mode = m.is_hifi() ? PAD_ZERO : PAD_REFLECT;
-    if ((rc = call(m.pre, lc))) return rc;
+    rc = FV_NOT_APPLICABLE;
+    if (chain_ok && m.layers[m.pre].Cout % 16 == 0 &&
+        tc2_up_split_in_ok(m.layers[m.stages[0].up], tcl(m.stages[0].up), Be, L, false)) {
+      LayerCall ls = lc;
+      ls.out_split = true; ls.out_slope = 0.1f;   // the slope of the LeakyReLU in front of ups[0] (hifigan.py:95)
+      rc = call(m.pre, ls);
+      if (rc == FV_OK) cur_split = true;
+    }
+    if (rc == FV_NOT_APPLICABLE) rc = call(m.pre, lc);
+    if (rc) return rc;
   }
   // Each stage can run in micro-batches of utterances (FV_L2_BUDGET_MB) sized so that the stage's intermediate
   // tensors stay resident in the 126 MB L2.  Utterances are independent, so this is pure scheduling.  Measured on
@@ -394,6 +429,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
     long long mb = l2_budget / (4 * out_per_utt * (long long)sizeof(float));
     if (mb < 1) mb = 1;
     if (mb > Be) mb = Be;
+    bool stage_fin_split = false;
     for (int b0 = 0; b0 < Be; b0 += (int)mb) {
       const int nb = (int)std::min<long long>(mb, Be - b0);
       const float* x_in_mb = cur + (long long)b0 * in_per_utt;
@@ -433,17 +469,31 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
         LayerCall lc;
         lc.x = x_in_mb; lc.y = bufY; lc.B = nb; lc.Lin = L; lc.lens = lens_at((int)s - 1, b0);
         lc.pre_slope = m.is_hifi() ? 0.1f : mslope;  // LRELU_SLOPE modules.py:9 / negative_slope melgan.py:30
+        lc.in_split = cur_split;                     // the previous stage / conv_pre left a split copy: TMA-fed, no loader warps
         if (split_stage) {   // the upsample layer's epilogue writes lrelu(y) pre-split for the three branches' first convs
           LayerCall ls = lc;
           ls.out_split = true; ls.out_slope = 0.1f;
           rc = call(sg.up, ls);
           if (rc == FV_NOT_APPLICABLE) {   // not on the tensor-core kernel: fp32 output, then one packing pass
             lc.y = bufH;
-            if ((rc = call(sg.up, lc))) return rc;
+            rc = call(sg.up, lc);
+            if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "upsample layer refused the split input it was planned for");
+            if (rc) return rc;
             if ((rc = pack_split(bufH, bufY, nb, sg.Cout, Lout, 0.1f))) return rc;
           } else if (rc) return rc;
-        } else if ((rc = call(sg.up, lc))) return rc;
+        } else {
+          rc = call(sg.up, lc);
+          if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "upsample layer refused the split input it was planned for");
+          if (rc) return rc;
+        }
       }
+      // fin_split: the last MRF branch emits the stage result itself (running sum + its share, LeakyReLU 0.1, split) into the
+      // dead stage-input buffer, so the next stage's upsample layer is TMA-fed too.
+      const bool fin_split = chain_ok && split_stage && s + 1 < m.stages.size() && nb == Be && b0 == 0 &&
+                             (sg.branches.size() == 1 || mrf_red) &&
+                             tc2_up_split_in_ok(m.layers[m.stages[s + 1].up], tcl(m.stages[s + 1].up), nb, Lout, true) &&
+                             tc2_up_split_in_ok(m.layers[m.stages[s + 1].up], tcl(m.stages[s + 1].up), nb, Lout, false);
+      stage_fin_split = fin_split;
       const int* sl = lens_at((int)s, b0);   // lengths of this stage's tensors
       if (m.is_hifi()) {
         // MRF: xs = sum_j resblock_j(y); x = xs / num_kernels (hifigan.py:97-103); s_out accumulates xs.
@@ -460,6 +510,13 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
             if (last && mrf_red && nb_br > 1) {   // 1/num_kernels folded into every branch, no read of the running sum
               acc = (j == 0) ? ACC_STORE_SCALE : ACC_RED_SCALE; div = (float)nb_br;
             } else if (last && j > 0) { acc = (j == nb_br - 1) ? ACC_ADD_DIV : ACC_ADD; div = (float)nb_br; }
+            const bool emit_fin = fin_split && last && j == nb_br - 1;   // this launch writes the stage result (split) into `cur`
+            const float* ysum = nullptr;
+            if (emit_fin) {
+              dst = cur;
+              acc = nb_br > 1 ? ACC_STORE_SCALE : ACC_STORE; div = (float)nb_br;
+              ysum = nb_br > 1 ? s_out : nullptr;
+            }
             if (br.units[u].c2 >= 0 && split_wide) {   // unfused unit on the split / TMA chain (conv_tc2 x 2)
               LayerCall l1;
               l1.x = bc; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = 0.1f;
@@ -470,8 +527,8 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
               LayerCall l2;
               l2.x = bufH; l2.y = dst; l2.res = bc; l2.B = nb; l2.Lin = Lout; l2.pre_slope = 0.1f;
               l2.in_split = true; l2.res_split = true; l2.res_slope = 0.1f;
-              l2.out_split = !last; l2.out_slope = 0.1f;
-              l2.acc_mode = acc; l2.acc_div = div;
+              l2.out_split = !last || emit_fin; l2.out_slope = 0.1f;
+              l2.acc_mode = acc; l2.acc_div = div; l2.ysum = ysum;
               rc = call(br.units[u].c2, l2);
               if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "split-chain conv2 was not applicable after planning");
               if (rc) return rc;
@@ -490,9 +547,9 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
                     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
                     cudaEventRecord(r.e0, st);
                   }
-                  const int io = !split_stage ? IO_F32 : (last ? IO_SPLIT_F32 : IO_SPLIT_SPLIT);
+                  const int io = !split_stage ? IO_F32 : ((last && !emit_fin) ? IO_SPLIT_F32 : IO_SPLIT_SPLIT);
                   const int frc = launch_fused_unit(bc, dst, bias(br.units[u].c1), bias(br.units[u].c2), *t1, *t2, nb,
-                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st, sl, io);
+                                                    la.Cin, (int)Lout, la.K, la.dil, 0.1f, acc, div, st, sl, io, ysum);
                   if (prof) {
                     if (frc == 0) { cudaEventRecord(r.e1, st); prof->recs.push_back(r); }
                     else { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -548,7 +605,12 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
       }
     }
     L = Lout;
-    std::swap(cur, other);  // cur = stage output
+    if (stage_fin_split) {
+      cur_split = true;     // `cur` already holds the stage result as a split copy (written by the last MRF branch)
+    } else {
+      std::swap(cur, other);  // cur = stage output (fp32)
+      cur_split = false;
+    }
   }
 
   if (m.is_hifi()) {  // F.leaky_relu(x) [slope 0.01!] -> conv_post -> tanh (hifigan.py:104-106)

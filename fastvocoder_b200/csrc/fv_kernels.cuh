@@ -50,6 +50,9 @@ struct ConvArgs {
   // is rebuilt from the split copy, whose baked slope is 1 / res_inv_slope.
   int x_split, res_split;
   float res_inv_slope;
+  // OUT_BCL_SPLIT with acc_mode ACC_STORE_SCALE: the LAST branch of an MRF stage emits the stage result itself,
+  // split(lrelu(ysum + v / acc_div)), where ysum is the fp32 running sum the other branches stored / red-added.
+  const float* ysum;
   long long x_bs, y_bs, res_bs;  // batch strides in floats
   // two-input form (L_PAIR): input channels >= cin_split come from x2 (own pre-activation); 0 = single input
   const float* x2;

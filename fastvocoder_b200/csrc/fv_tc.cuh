@@ -754,6 +754,11 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
     }
     if (it + ngrp < n_it) fetch(it + ngrp);
     float* py = opaque_ptr(yb + (ok ? o0 : 0));
+    if (OS && a.ysum) {   // last MRF branch: (v + ysum * num_kernels) / num_kernels, loads in flight before the TMEM read
+      const float* ps = opaque_ptr(a.ysum + (long long)b * a.res_bs + (ok ? o0 : 0));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) addend[i] = fmaf(ok ? __ldg(ps + (uint32_t)i * uos) : 0.f, a.acc_div, addend[i]);
+    }
     if (!OS && acc_reads_y(a.acc_mode)) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) addend[i] += ok ? py[(uint32_t)i * uos] : 0.f;
@@ -790,11 +795,13 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
         }
       }
       if (OS) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (__uint_as_float(rr[i]) + addend[i]) * inv;
         uint32_t hp[8], lp[8];
 #pragma unroll
         for (int i = 0; i < 16; i += 2)
-          split_f16x2(lrelu01(__uint_as_float(rr[i]) + addend[i], a.out_slope),
-                      lrelu01(__uint_as_float(rr[i + 1]) + addend[i + 1], a.out_slope), hp[i >> 1], lp[i >> 1]);
+          split_f16x2(lrelu01(v[i], a.out_slope), lrelu01(v[i + 1], a.out_slope), hp[i >> 1], lp[i >> 1]);
         uint4* yq = opaque_ptr(reinterpret_cast<uint4*>(yb) + ((uint32_t)(nbase >> 3) * uos + (uint32_t)pos));
         yq[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         yq[uos] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
@@ -1203,7 +1210,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   static const int force_mt_xs = getenv("FV_TC2_MT_XS") ? atoi(getenv("FV_TC2_MT_XS")) : 0;   // tuning knob: M tiles per CTA tile, split-input layers
   if ((a.res != nullptr || a.acc_mode != ACC_STORE) && ((a.out_layout != OUT_BCL && a.out_layout != OUT_BCL_SPLIT) || a.post_tanh)) return false;
   if (a.out_layout == OUT_BCL_SPLIT &&
-      (a.acc_mode != ACC_STORE || a.N % 16 || L.n_pad != a.N || a.post_tanh || !(a.out_slope >= 0.f && a.out_slope <= 1.f) ||
+      (!(a.acc_mode == ACC_STORE || (a.acc_mode == ACC_STORE_SCALE && a.res != nullptr)) || a.N % 16 || L.n_pad != a.N || a.post_tanh || !(a.out_slope >= 0.f && a.out_slope <= 1.f) ||
        (a.res != nullptr && !a.res_split)))
     return false;
   if (a.res_split && (a.res == nullptr || a.N % 16 || !(a.res_inv_slope >= 1.f))) return false;
@@ -1365,9 +1372,13 @@ inline void tc_apply_env_once() {
 // FV_PDL=1: launch the tensor-core kernels of the layer chain with programmatic stream serialization (the next
 // layer's prologue overlaps this layer's tail).  Correct (GPU tests pass with it) but measured neutral-to-slower on the
 // B=32 step (19.7 -> 20.1 ms, profiles/r01_notes.md "ab2"), so it stays opt-in.
-inline bool tc_pdl_enabled() {
-  static const bool on = getenv("FV_PDL") != nullptr && atoi(getenv("FV_PDL")) != 0;
-  return on;
+// Default (FV_PDL unset): on for LATENCY-bound launches only — few tiles per CTA, i.e. small batches / the batch-1 path, where
+// the next kernel's prologue (barrier init, TMEM alloc, resident weight images) is a visible share of a ~20-30 us launch
+// (measured, T = 1000 batch 1: HiFi-GAN 1.52 -> 1.42 ms eager, 1.45 -> 1.40 ms graph replay; profiles/r02_notes.md).
+inline bool tc_pdl_enabled(long long total_tiles = 0, int num_sms = 148) {
+  static const int mode = getenv("FV_PDL") ? atoi(getenv("FV_PDL")) : -1;
+  if (mode >= 0) return mode != 0;
+  return total_tiles > 0 && total_tiles <= 4LL * num_sms;
 }
 
 // FV_STALL_DEBUG=1: launch the instrumented instantiation, synchronise and print where each role waited (stderr).
@@ -1478,7 +1489,7 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  p.pdl = (tc_pdl_enabled() && cs == 1 && !tc_stall_debug()) ? 1 : 0;
+  p.pdl = (tc_pdl_enabled(p.total_tiles, num_sms[dev]) && cs == 1 && !tc_stall_debug()) ? 1 : 0;
   if (p.pdl) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
@@ -1558,6 +1569,7 @@ struct Tc3Args {
   // same planes (x = unlrelu(hi + lo)); IO_SPLIT_SPLIT units write their output in the same format for the next unit.
   const void* xs;
   void* ys;
+  const float* ysum;       // IO_SPLIT_SPLIT only: fp32 running MRF sum added after the 1/num_kernels scaling (last branch)
   float inv_slope;         // 1 / slope (slope > 0): undoes the LeakyReLU baked into the split copy
   int x_rows_alloc;        // row stride of the A1 planes (x_rows rounded up to 8 in split mode: 128-B aligned TMA boxes)
   int epi_groups;          // split mode: 1 or 2 warps per TMEM lane quarter in each of epiA / epiB
@@ -2082,6 +2094,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 #pragma unroll
               for (int i = 0; i < 16; ++i) xv[i] += ok ? py[(uint32_t)i * uL] : 0.f;
             }
+            if (IO == IO_SPLIT_SPLIT && p.ysum) {
+              // last branch of the stage: result = ysum + v / num_kernels = (v + ysum * num_kernels) / num_kernels — folded into
+              // the addend here so that the loads are in flight before the accumulator wait (no extra registers)
+              const float* ps = opaque_ptr(p.ysum + (long long)b * C * p.L + (ok ? o0 : 0));
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xv[i] = fmaf(ok ? __ldg(ps + (uint32_t)i * uL) : 0.f, p.acc_div, xv[i]);
+            }
             if (!waited) {
               wa.wait(0, BAR(10 + bs), (uint32_t)((it / p.acc2_stages) & 1), 880 + bs);
               tc_fence_after();
@@ -2295,16 +2314,17 @@ inline bool tc3_split_available() { return tma_encode_fn() != nullptr; }
 // IO_SPLIT_SPLIT, so is y (acc_mode must be ACC_STORE); lens (ragged batches) is not supported in split mode.
 inline int launch_fused_unit(const float* x, float* y, const float* b1, const float* b2, const TcLayer& l1,
                              const TcLayer& l2, int B, int C, int L, int K, int dil, float slope, int acc_mode,
-                             float acc_div, cudaStream_t st, const int* lens = nullptr, int io = IO_F32) {
+                             float acc_div, cudaStream_t st, const int* lens = nullptr, int io = IO_F32,
+                             const float* ysum = nullptr) {
   if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
   tc_apply_env_once();
   Tc3Args p{};
   if (!(slope >= 0.f && slope <= 1.f)) return 1;   // lrelu01
   if (io != IO_F32 && (lens != nullptr || !(slope > 0.f) || !tc3_split_available())) return 1;
-  if (io == IO_SPLIT_SPLIT && acc_mode != ACC_STORE) return 1;
+  if (io == IO_SPLIT_SPLIT && !(acc_mode == ACC_STORE || (acc_mode == ACC_STORE_SCALE && ysum != nullptr))) return 1;
   if (!tc3_plan(B, C, L, K, dil, p, io != IO_F32)) return 1;
   p.x = x; p.y = y; p.bias1 = b1; p.bias2 = b2; p.lens = lens;
-  p.xs = x; p.ys = y;
+  p.xs = x; p.ys = y; p.ysum = (io == IO_SPLIT_SPLIT) ? ysum : nullptr;
   p.inv_slope = slope > 0.f ? 1.0f / slope : 1.0f;
   static const int epi_env = getenv("FV_TC3_EPI") ? atoi(getenv("FV_TC3_EPI")) : 2;   // epilogue warp groups in split mode
   p.epi_groups = (io != IO_F32 && epi_env >= 2) ? 2 : 1;
@@ -2353,7 +2373,7 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
   cfg.dynamicSmemBytes = tc3_smem_bytes(p);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  p.pdl = (tc_pdl_enabled() && !tc_stall_debug()) ? 1 : 0;
+  p.pdl = (tc_pdl_enabled(p.total_tiles, num_sms[dev]) && !tc_stall_debug()) ? 1 : 0;
   if (p.pdl) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

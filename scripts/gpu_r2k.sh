@@ -1,0 +1,25 @@
+#!/bin/bash
+# round 2, call K: split chain across stages (conv_pre / last MRF branch emit split, upsample layers TMA-fed) — parity, then A/B
+OUT=gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x -k "model_forward or model_inference or batch_equals or bench_shapes or ragged or cuda_graph or synthesizer or publish or edge_lengths or full_size or config0" 2>&1 | tail -8 > $OUT/r2k_pytest.log
+cat $OUT/r2k_pytest.log
+ab() { # label model env...
+  label=$1; m=$2; shift 2
+  env "$@" timeout 300 python bench.py --model $m --steps 10 --warmup 3 --skip-cpu-baseline --headline-only --profile-out $OUT/r2k_layers_${m}_$label.json > $OUT/r2k_bench_${m}_$label.json 2> $OUT/r2k_bench_${m}_$label.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/r2k_bench_${m}_$label.json").read().strip().splitlines()[-1])
+    L=json.load(open("$OUT/r2k_layers_${m}_$label.json"))["layers"]
+    ups=sum(x["ms"] for x in L if x["name"].startswith("ups") or x["name"].startswith("conv_p"))
+    last=sum(x["ms"] for x in L if x["K"]==11 and x["dil"]==5)
+    print("%-18s %-8s ms/step %.2f clk %s | ups+pre+post %.3f | k11 d5 units/convs %.3f | sum %.2f"%("$m", "$label", d["ms_per_step"], d["clocks"]["sm_mhz"], ups, last, sum(x["ms"] for x in L)))
+except Exception as e:
+    print("$m $label", "bench failed", e); print(open("$OUT/r2k_bench_${m}_$label.err").read()[-1500:])
+PY
+}
+ab fin1 hifigan FV_X=0
+ab fin0 hifigan FV_SPLIT_FINAL=0
+ab fin1 multiband-hifigan FV_X=0
+ab fin0 multiband-hifigan FV_SPLIT_FINAL=0
+ab fin1b hifigan FV_X=0
