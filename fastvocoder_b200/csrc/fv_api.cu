@@ -109,6 +109,7 @@ struct LayerCall {
   bool in_split = false, res_split = false;
   float res_slope = 0.f;
   const float* ysum = nullptr;   // split output of the last MRF branch: fp32 running sum of the other branches
+  bool x1_split = false;         // L_PAIR: the first input (h) is a split copy fetched by TMA, the second stays fp32
 };
 constexpr int FV_NOT_APPLICABLE = 1;   // positive: not an error, the caller takes its fallback
 
@@ -183,8 +184,10 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
   // HBM-bound k = 7 single-channel output convs (conv_post 16->1, LastLayer 32->1): the streaming kernel on both paths
   // (measured 0.305 -> 0.148 ms / 0.457 -> 0.265 ms = 3.5-3.8 TB/s).  The 64->4 conv_post of Multiband-HiFi-GAN is FMA-bound
   // there (0.56 ms) and stays on tcgen05 (0.47 ms) when tensor cores are allowed.
-  if (c.out_split || c.in_split || c.res_split) {
+  if (c.out_split || c.in_split || c.res_split || c.x1_split) {
     if (!c.allow_tc || tc_disabled || !tcl || !tcl->eligible || c.lens) return FV_NOT_APPLICABLE;
+    if (c.x1_split && l.type != L_PAIR) return FV_NOT_APPLICABLE;
+    a.x1_split = c.x1_split ? 1 : 0;
     if (a.out_layout != OUT_PHASE && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
     if (c.res_split && a.out_layout != OUT_BCL) return FV_NOT_APPLICABLE;
     if (c.out_split) a.out_layout = a.out_layout == OUT_PHASE ? OUT_PHASE_SPLIT : OUT_BCL_SPLIT;
@@ -245,6 +248,31 @@ static bool tc2_up_split_in_ok(const Layer& l, const TcLayer* t, int nb, long lo
   a.acc_mode = ACC_STORE;
   Tc2Args p{};
   return a.pad_left >= 0 && tc2_plan(a, *t, p, 148);
+}
+
+// ResidualStack on the hybrid split path: would conv_tc2 take the dilated conv with a split (pre-activated) OUTPUT, and the
+// fused pair 1x1 with its first input (that h) fetched by TMA?
+static bool tc2_stack_split_ok(const Model& m, const Stack& sk, const TcLayer* td, const TcLayer* tp, int nb, long long L,
+                               float slope) {
+  if (sk.pair < 0 || !td || !tp || !td->eligible || !tp->eligible) return false;
+  const Layer& d = m.layers[sk.dil_conv];
+  const Layer& pl = m.layers[sk.pair];
+  if (d.Cout % 16 || td->n_pad != d.N || !(slope >= 0.f && slope <= 1.f)) return false;
+  Tc2Args p{};
+  ConvArgs a{};
+  a.B = nb; a.Cin = d.Cin; a.N = d.N; a.Lin = (int)L; a.Lpos = (int)L; a.K = d.Kd; a.dil = d.dil;
+  a.pad_mode = PAD_REFLECT; a.pad_left = d.causal ? (d.K - 1) * d.dil : (d.K - 1) * d.dil / 2; a.pre_slope = slope;
+  a.out_layout = OUT_BCL_SPLIT; a.out_slope = slope; a.bias_mod = d.Cout;
+  a.x_bs = (long long)d.Cin * L; a.y_bs = a.res_bs = (long long)d.Cout * L; a.acc_mode = ACC_STORE;
+  if (!tc2_plan(a, *td, p, 148)) return false;
+  ConvArgs q{};
+  q.B = nb; q.Cin = pl.Cin; q.N = pl.N; q.Lin = (int)L; q.Lpos = (int)L; q.K = 1; q.dil = 1;
+  q.pad_mode = PAD_ZERO; q.pad_left = 0; q.pre_slope = slope; q.pre_slope2 = -1.f;
+  q.out_layout = OUT_BCL; q.bias_mod = pl.Cout; q.cin_split = pl.Cout; q.x1_split = 1;
+  q.x2 = reinterpret_cast<const float*>(0x10);
+  q.x_bs = q.x2_bs = (long long)pl.Cout * L; q.y_bs = q.res_bs = (long long)pl.Cout * L; q.acc_mode = ACC_STORE;
+  Tc2Args p2{};
+  return tc2_plan(q, *tp, p2, 148);
 }
 
 // ---- whole-model forward ----------------------------------------------------------------------------
@@ -584,14 +612,25 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
         for (int k = 0; k < ns; ++k) {  // ResidualStack (modules.py:372-382)
           const Stack& sk = sg.stacks[k];
           float* dst = (k == ns - 1) ? s_out : (k % 2 ? bufY : bufU1);
+          // hybrid split path: the dilated conv writes h pre-activated in the split format and the pair layer fetches those
+          // chunks by TMA (bit-identical A operand: the loader computed the same lrelu + hi/lo split); FV_STACK_SPLIT=0: off
+          static const bool stack_split_env = getenv("FV_STACK_SPLIT") == nullptr || atoi(getenv("FV_STACK_SPLIT")) != 0;
+          const bool h_split = pair_ok && tc_ok && split_env0 && stack_split_env && !lens_dev && tc3_split_available() &&
+                               tc2_stack_split_ok(m, sk, tcl(sk.dil_conv), sk.pair >= 0 ? tcl(sk.pair) : nullptr, nb, Lout, mslope);
           LayerCall l1;
           l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = mslope; l1.pad_mode = PAD_REFLECT; l1.lens = sl;
-          if ((rc = call(sk.dil_conv, l1))) return rc;
+          l1.out_split = h_split; l1.out_slope = mslope;
+          rc = call(sk.dil_conv, l1);
+          if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "stack conv refused the split output it was planned for");
+          if (rc) return rc;
           if (pair_ok && sk.pair >= 0) {   // stack.4(lrelu(h)) + skip_layer(c) as one two-input 1x1 GEMM-conv
             LayerCall lp;
             lp.x = bufH; lp.pre_slope = mslope; lp.x2 = sc_in; lp.pre_slope2 = -1.f;
             lp.y = dst; lp.B = nb; lp.Lin = Lout; lp.lens = sl;
-            if ((rc = call(sk.pair, lp))) return rc;
+            lp.x1_split = h_split;
+            rc = call(sk.pair, lp);
+            if (rc == FV_NOT_APPLICABLE) return fail(FV_ESTATE, "pair layer refused the split input it was planned for");
+            if (rc) return rc;
           } else {
             LayerCall ls;
             ls.x = sc_in; ls.y = bufU0; ls.B = nb; ls.Lin = Lout; ls.lens = sl;

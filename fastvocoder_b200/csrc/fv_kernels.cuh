@@ -50,6 +50,9 @@ struct ConvArgs {
   // is rebuilt from the split copy, whose baked slope is 1 / res_inv_slope.
   int x_split, res_split;
   float res_inv_slope;
+  // two-input (pair) layers on the tensor-core kernel: the FIRST input (channels < cin_split: h of the ResidualStack, written
+  // pre-activated in the split format by the dilated conv) is fetched by TMA, the second (the raw stack input) by the loaders
+  int x1_split;
   // OUT_BCL_SPLIT with acc_mode ACC_STORE_SCALE: the LAST branch of an MRF stage emits the stage result itself,
   // split(lrelu(ysum + v / acc_div)), where ysum is the fp32 running sum the other branches stored / red-added.
   const float* ysum;

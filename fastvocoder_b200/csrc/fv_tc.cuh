@@ -334,7 +334,9 @@ constexpr int LD_MAX = 5;
 // address arithmetic was the largest part).
 template <bool ACT01 = false, class Src>
 __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, int rows, int nkc, int ltid, int per,
-                                                int rounds, int g0, int Lb, int lstride, bool reflect, Src src) {
+                                                int rounds, int g0, int Lb, int lstride, bool reflect, Src src,
+                                                int plane_rows = 0) {
+  if (plane_rows == 0) plane_rows = rows;   // row stride of the 8-channel planes in shared memory (>= rows)
   const int nitems = nkc * rows;
   const uint32_t ls = (uint32_t)lstride;   // unsigned: keeps c * ls a 32-bit multiply feeding one IMAD.WIDE.U32
   const int kstep = 256 / rows, rstep = 256 - kstep * rows;   // item + 256 -> (kc + kstep, r + rstep) with one carry
@@ -359,7 +361,7 @@ __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, in
       const float* pg = opaque_ptr(xc + (ok ? g : 0));
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(pg + (uint32_t)c * ls) : 0.f;
-      ofs[t] = live ? (kc * rows + r0) * 16 : -1;
+      ofs[t] = live ? (kc * plane_rows + r0) * 16 : -1;
       if (t < per) {   // advance to item i0 + 256
         i0 += 256; kc0 += kstep; r0 += rstep;
         if (r0 >= rows) { r0 -= rows; ++kc0; }
@@ -413,8 +415,10 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __
 
 inline int tc_pick_nt(int N) {
   if (N % 16) return 0;
-  if (N <= 256) return N;
-  for (int nt = 256; nt >= 16; nt -= 16)
+  static const int nt_max = getenv("FV_NT_MAX") ? atoi(getenv("FV_NT_MAX")) : 256;   // tuning knob: widest N tile
+  const int cap = (nt_max >= 16 && nt_max <= 256) ? nt_max / 16 * 16 : 256;
+  if (N <= cap) return N;
+  for (int nt = cap; nt >= 16; nt -= 16)
     if (N % nt == 0) return nt;
   return 0;
 }
@@ -929,6 +933,30 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         if (u >= p.a_stages) wa.wait(0, BAR(2 + s), (uint32_t)((u / p.a_stages - 1) & 1), 400 + s);
         uint8_t* A_hi = Abuf + (size_t)s * 2 * a_bytes;
         uint8_t* A_lo = A_hi + a_bytes;
+        if (a.x1_split && ch * p.ck < a.cin_split) {
+          // hybrid stage: this chunk of the pair layer's first input (h, split format) arrives by TMA — warp 0 issues the
+          // boxes, its expect_tx is its arrival; the other loader warps just arrive (the barrier still counts 8 + the bytes)
+          if (warp == 0) {
+            const int nfull = rows / TMA_SPLIT_RB, tail = rows - nfull * TMA_SPLIT_RB;
+            const int nrb = nfull + (tail ? 1 : 0);
+            const int per_half = nkc * nrb, nops = 2 * per_half, planes_b = a.cin_split >> 3;
+            const int g0 = t0 - a.pad_left;
+            if (lane == 0) mbar_expect_tx(BAR(0 + s), (uint32_t)(2 * nkc * rows * 16));
+            __syncwarp();
+            const uint32_t a_hi = smem_u32(A_hi);
+            for (int i = lane; i < nops; i += 32) {
+              const int half = i >= per_half ? 1 : 0;
+              const int rem = i - half * per_half;
+              const int kc = rem / nrb, rb = rem - kc * nrb;
+              const uint32_t dst = a_hi + (uint32_t)half * a_bytes + (uint32_t)(kc * p.rows_alloc + rb * TMA_SPLIT_RB) * 16u;
+              tma_load_2d(dst, rb < nfull ? &tm_main : &tm_tail, 2 * (g0 + rb * TMA_SPLIT_RB),
+                          (b * 2 + half) * planes_b + ch * nkc + kc, BAR(0 + s));
+            }
+          } else {
+            if (lane == 0) mbar_arrive(BAR(0 + s));
+          }
+          continue;
+        }
         if (p.ld_per > 0) {
           fill_stage_flat(A_hi, A_lo, rows, nkc, warp * 32 + lane, p.ld_per, p.ld_rounds, t0 - a.pad_left, Lb,
                           a.Lin, a.pad_mode == PAD_REFLECT, [&](int kc, const float*& xc, float& slope) {
@@ -937,7 +965,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
                             xc = second ? a.x2 + (long long)b * a.x2_bs + (long long)(cg - a.cin_split) * a.Lin
                                         : xb + (long long)cg * a.Lin;
                             slope = second ? a.pre_slope2 : a.pre_slope;
-                          });
+                          }, p.rows_alloc);
         } else
         for (int pr = warp; pr < npairs; pr += TC2_LOADER_WARPS) {
           const int kc = pr / nrb, rbk = pr - kc * nrb;
@@ -969,7 +997,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 #pragma unroll
             for (int c = 0; c < 8; c += 2) split_f16x2(pre_act(v[t][c], slope), pre_act(v[t][c + 1], slope),
                                                        hp[c >> 1], lp[c >> 1]);
-            const uint32_t off = ((uint32_t)kc * rows + rrow[t]) * 16;
+            const uint32_t off = ((uint32_t)kc * p.rows_alloc + rrow[t]) * 16;
             *reinterpret_cast<uint4*>(A_hi + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             *reinterpret_cast<uint4*>(A_lo + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
           }
@@ -1218,7 +1246,10 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   if (a.x_split && (a.pad_mode != PAD_ZERO || a.cin_split != 0 || a.lens != nullptr || a.Cin % 16 ||
                     a.x_bs != (long long)a.Cin * a.Lin || !tma_encode_fn()))
     return false;
-  auto xr = [&](long long rows) { return a.x_split ? (rows + 7) / 8 * 8 : rows; };   // 128-byte aligned TMA boxes
+  if (a.x1_split && (a.x_split || a.cin_split <= 0 || a.cin_split % 16 || a.pad_mode != PAD_ZERO || a.pad_left != 0 || a.K != 1 ||
+                     a.lens != nullptr || a.x_bs != (long long)a.cin_split * a.Lin || !tma_encode_fn()))
+    return false;
+  auto xr = [&](long long rows) { return (a.x_split || a.x1_split) ? (rows + 7) / 8 * 8 : rows; };   // 128-byte aligned TMA boxes
   {  // the kernels index inside one utterance's input / output plane with 32-bit element offsets
     const long long lim = 0x7fffffffLL - 65536;
     const long long out_plane = (a.out_layout == OUT_PHASE || a.out_layout == OUT_PHASE_SPLIT) ? (long long)a.ph_cout * a.ph_lout
@@ -1262,6 +1293,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
       const int ck = ck_opts[cki];
       if (ck > a.Cin || a.Cin % ck || ck % 16 || (cki > 0 && ck == a.Cin)) continue;
       if (phase == 1 && ck != ck_fixed) continue;
+      if (a.x1_split && a.cin_split % ck) continue;   // a TMA-fed chunk must not straddle the two inputs
       const int nck = a.Cin / ck, kpc = ck / 16;
       int kbps = 16384 / kblock_bytes;
       if (kbps < 1) kbps = 1;
@@ -1287,8 +1319,9 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
               const double t_mma = std::max((double)kblocks * mt * c_pipe, (double)kblocks * my_mts * n_umma * 20.0);
               const int rows_t = mt * 128 + halo;
               const int pairs = (ck / 8) * ((rows_t + 127) / 128);
-              const double t_load = a.x_split ? nck * (double)rows_t * ck * 4.0 / 40.0   // TMA: bandwidth only, no loader rounds
-                                              : nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
+              double t_load = a.x_split ? nck * (double)rows_t * ck * 4.0 / 40.0   // TMA: bandwidth only, no loader rounds
+                                        : nck * (((pairs + 7) / 8) * 2500.0 + (double)rows_t * ck * 4.0 / 40.0);
+              if (a.x1_split) t_load *= (double)(a.Cin - a.cin_split) / a.Cin;   // only the second input goes through the loaders
               const double ring_bw = std::min(14.0, (double)wb / 2500.0);
               const double t_w = res ? 0.0 : (double)w_total / ring_bw;
               const double t_epi = (double)mt * 128 * NT *
@@ -1457,8 +1490,8 @@ inline int launch_conv_tc2(const ConvArgs& a, const TcLayer& L, cudaStream_t st)
   CUtensorMap tm_main, tm_tail;
   memset(&tm_main, 0, sizeof tm_main);
   memset(&tm_tail, 0, sizeof tm_tail);
-  if (a.x_split) {
-    const long long planes = (long long)a.B * 2 * (a.Cin / 8);
+  if (a.x_split || a.x1_split) {
+    const long long planes = (long long)a.B * 2 * ((a.x1_split ? a.cin_split : a.Cin) / 8);
     const int tail = p.rows % TMA_SPLIT_RB;
     if (!tma_encode_split(&tm_main, a.x, a.Lin, planes, TMA_SPLIT_RB)) return 1;
     if (tail) {

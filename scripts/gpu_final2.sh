@@ -20,9 +20,16 @@ kill $SMI
 B="python bench.py --steps 1 --warmup 3 --skip-cpu-baseline --headline-only"
 # ncu: launch list of the bench command (cold-cache, serialised: compare shares), then full captures at --batch 8
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $B > $OUT/ncu_launch_$TAG.log 2>&1
+# gpurun merges at most 64 MiB back: every capture is reduced ON THE BOX to its raw-page csv + the text summary; the .ncu-rep
+# itself is kept for the three kernels DESIGN.md discusses (no --import-source: the SASS listings are committed separately)
+KEEP="fused_c32k7 tc2_c128k11 narrow7"
 cap() { # name, kernel regex, skip, extra bench args...
   n=$1; k=$2; s=$3; shift 3
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $s -c 1 -o $OUT/ncu_${n}_$TAG $B "$@" > $OUT/ncu_${n}_$TAG.log 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:$k -s $s -c 1 -o $OUT/ncu_${n}_$TAG $B "$@" > $OUT/ncu_${n}_$TAG.log 2>&1
+  ncu -i $OUT/ncu_${n}_$TAG.ncu-rep --page raw --csv > $OUT/ncu_${n}_$TAG.raw.csv 2>/dev/null
+  python scripts/ncu_summary.py $OUT/ncu_${n}_$TAG.ncu-rep > $OUT/ncu_${n}_$TAG.txt 2>&1
+  case " $KEEP " in *" $n "*) ;; *) rm -f $OUT/ncu_${n}_$TAG.ncu-rep ;; esac
+  tail -c 300 $OUT/ncu_${n}_$TAG.log > $OUT/ncu_${n}_$TAG.log.tail; rm -f $OUT/ncu_${n}_$TAG.log
 }
 cap fused_c32k7 conv_tc3 12 --batch 8          # TMA-fed split fused unit, C=32 k=7 (resident weights, ping-pong tiles)
 cap fused_c16k3 conv_tc3 18 --batch 8          # C=16 k=3
@@ -44,4 +51,4 @@ for m in ("hifigan","basis-melgan","multiband-hifigan","melgan","hifigan_fp32pat
     except Exception as e:
         print(m, "failed", e)
 PY
-ls -la $OUT/*_$TAG.ncu-rep
+ls -la $OUT/*_$TAG.ncu-rep $OUT/*_$TAG.raw.csv; du -sh $OUT

@@ -629,8 +629,9 @@ def test_batch_equals_single_at_full_length(specs, key):
             assert torch.equal(yb[b:b + 1], ys), (key, b, float((yb[b:b + 1] - ys).abs().max()))
 
 
-KNOBS = [{"FV_SPLIT": "0"}, {"FV_TC3_EPI": "1"}, {"FV_TC3_PP": "0"}, {"FV_TC3_PP": "3"}, {"FV_TC3_RING": "0"},
-         {"FV_MRF_RED": "0"}, {"FV_TC3_ISSUERS": "1"}, {"FV_PDL": "1"}, {"FV_NO_FUSE": "1"}]
+KNOBS = [{"FV_SPLIT": "0"}, {"FV_SPLIT_WIDE": "0"}, {"FV_SPLIT_FINAL": "0"}, {"FV_STACK_SPLIT": "0"}, {"FV_TC3_EPI": "1", "FV_TC2_EPI": "1"},
+         {"FV_TC3_PP": "0"}, {"FV_TC3_PP": "3"}, {"FV_TC3_RING": "0"}, {"FV_MRF_RED": "0"}, {"FV_TC3_ISSUERS": "1"}, {"FV_PDL": "1"},
+         {"FV_PDL": "0"}, {"FV_NO_FUSE": "1"}]
 
 
 @pytest.mark.parametrize("knob", KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
@@ -640,8 +641,8 @@ def test_planner_knobs_keep_parity(knob):
     import subprocess
     import sys
     env = dict(os.environ, **knob)
-    sel = "(test_model_forward_matches_reference and hifigan-l)"
-    if not ({"FV_TC3_RING", "FV_NO_FUSE", "FV_SPLIT"} & set(knob)):   # those knobs turn (part of) the fused-unit kernel off: the
+    sel = "(test_model_forward_matches_reference and (hifigan-l or melgan-original or basis-melgan-light))"
+    if not ({"FV_TC3_RING", "FV_NO_FUSE", "FV_SPLIT", "FV_STACK_SPLIT", "FV_SPLIT_WIDE", "FV_SPLIT_FINAL"} & set(knob)):   # those knobs turn (part of) the fused-unit kernel off: the
         sel += " or test_fused_resblock1_unit_kernel"                # unit-level entry point then refuses the shape (by design)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(REPO, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu",
                           "-k", sel], capture_output=True, text=True, cwd=REPO, env=env, timeout=900)
