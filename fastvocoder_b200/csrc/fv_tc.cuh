@@ -572,6 +572,7 @@ struct Tc2Args {
   int tmem_cols, acc_cols;
   int tiles_per_batch, total_tiles;
   int ck, nck;       // K-chunking: an A stage holds `ck` input channels of the tile; nck = Cin / ck stages per tile
+  int acc_per_mt;    // single accumulator set, one M tile per issuer: accumulators are handed back per M tile (epilogue M-tile-major)
   int rows_alloc;    // row stride of the A planes (= rows; rounded up to 8 with a split / TMA-fed input: 128-B aligned boxes)
   int epi_groups;    // split input: warps 4-7 are a second epilogue group (no loader warps then)
   int cluster_mode;  // experimental (FV_CLUSTER): 1 = pairs, private weight copies; 2 = each CTA multicasts its half; 3 = rank 0 multicasts all
@@ -593,10 +594,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // tcgen05.ld -> + bias -> [tanh] -> coalesced stores (ConvTranspose: phase interleave; narrow layers: masked tail columns).
 template <int LAYOUT, bool DBG>
 __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                  int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1) {
+                                                  int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1, int mt_lo = 0,
+                                                  int mt_hi = -1) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const int nchunks = p.NT >> 4;
+  if (mt_hi < 0) mt_hi = p.m_tiles;
   for (int c = 0; c < nchunks; ++c) {
     const int nbase = nt * p.NT + c * 16;
     constexpr bool PHASED = (LAYOUT == OUT_PHASE || LAYOUT == OUT_PHASE_SPLIT);
@@ -614,7 +617,7 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
 #pragma unroll
       for (int i = 0; i < 16; ++i) bias[i] = 0.f;
     }
-    for (int mt = 0; mt < p.m_tiles; ++mt) {
+    for (int mt = mt_lo; mt < mt_hi; ++mt) {
       if (ngrp == 2 && ((c * p.m_tiles + mt) & 1) != grp) continue;   // the lane quarter's other epilogue warp takes it
       const int pos = t0 + mt * 128 + q * 32 + lane;
       uint32_t rr[16];
@@ -706,12 +709,15 @@ __device__ __forceinline__ void tc2_epilogue_tile(const Tc2Args& p, uint32_t tme
 // OS: the output is written LeakyReLU(out_slope)-activated in the split format (the next unit's TMA-fed input).
 template <bool DBG, bool RS, bool OS>
 __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t tmem_acc, int q, int lane, int b, int t0,
-                                                      int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1) {
+                                                      int nt, WaitAcc<DBG>& wa, int grp = 0, int ngrp = 1, int mt_lo = 0,
+                                                      int mt_hi = -1) {
   const ConvArgs& a = p.a;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const float* __restrict__ rb = a.res ? a.res + (long long)b * a.res_bs : nullptr;
   const int nchunks = p.NT >> 4;
-  const int n_it = nchunks * p.m_tiles;          // iteration = (chunk c, M tile mt), mt fastest
+  if (mt_hi < 0) mt_hi = p.m_tiles;
+  const int mts = mt_hi - mt_lo;
+  const int n_it = nchunks * mts;                // iteration = (chunk c, M tile mt), mt fastest
   // xs / num_kernels (hifigan.py:103) as a multiply by the fp32 reciprocal: <= 1 ulp from the division, far inside 1e-4
   const float inv = (a.acc_mode == ACC_ADD_DIV || a.acc_mode >= ACC_STORE_SCALE) ? 1.0f / a.acc_div : 1.0f;
   const bool red = a.acc_mode == ACC_RED_SCALE;
@@ -725,7 +731,7 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
   float nxt[RS ? 1 : 16];
   uint4 nq[RS ? 4 : 1];
   auto fetch = [&](int it2) {
-    const int c2 = it2 / p.m_tiles, mt2 = it2 - c2 * p.m_tiles;
+    const int c2 = it2 / mts, mt2 = mt_lo + (it2 - c2 * mts);
     const int pos2 = t0 + mt2 * 128 + row;
     const bool ok2 = rb != nullptr && pos2 < a.Lpos;
     const int nb2 = nt * p.NT + c2 * 16;
@@ -741,7 +747,7 @@ __device__ __forceinline__ void tc2_epilogue_tile_add(const Tc2Args& p, uint32_t
   };
   if (grp < n_it) fetch(grp);
   for (int it = grp; it < n_it; it += ngrp) {
-    const int c = it / p.m_tiles, mt = it - c * p.m_tiles;
+    const int c = it / mts, mt = mt_lo + (it - c * mts);
     const int nbase = nt * p.NT + c * 16;
     const int pos = t0 + mt * 128 + row;
     const bool ok = pos < a.Lpos;
@@ -844,7 +850,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
   //              [24,32) w_free (cluster mode: every CTA's issuers are done with the slot)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  //              [32,40) acc_mt_empty[acc stage][M tile] (acc_per_mt plans: the epilogue hands the accumulators back per M tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform -> uniform-register code
@@ -867,6 +874,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       mbar_init(BAR(4 + s), p.n_issuers);   // acc_full: one tcgen05.commit per issuer
       mbar_init(BAR(6 + s), 4 * epi_groups);   // acc_empty: one arrive per epilogue warp
     }
+    for (int s = 0; s < 8; ++s) mbar_init(BAR(32 + s), 4 * epi_groups);   // acc_mt_empty: one arrive per epilogue warp
     for (int s = 0; s < 8; ++s) {
       mbar_init(BAR(8 + s), 1);                // w_full: expect_tx by the producer
       mbar_init(BAR(16 + s), p.n_issuers);     // w_empty: one (local) tcgen05.commit per issuer
@@ -1100,7 +1108,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
         int it = 0, g = 0, u = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
           const int as = it % p.acc_stages;
-          if (it >= p.acc_stages) wa.wait(1, BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
+          // acc_per_mt: this issuer owns exactly one M tile and restarts as soon as the epilogue has drained THAT tile's columns
+          if (it >= p.acc_stages)
+            wa.wait(1, p.acc_per_mt ? BAR(32 + as * 4 + wid) : BAR(6 + as), (uint32_t)((it / p.acc_stages - 1) & 1), 620 + as);
           const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols) + (uint32_t)wid * acc_mt_cols;
           for (int ch = 0; ch < p.nck; ++ch, ++u) {
             const int s = u % p.a_stages;
@@ -1198,14 +1208,26 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
       const int t0 = (tile - b * p.tiles_per_batch) * M;
       const uint32_t acc = tmem_base + (uint32_t)(as * p.acc_cols);
       const bool has_add = a.res != nullptr || a.acc_mode != ACC_STORE;
-      if (a.out_layout == OUT_BCL_SPLIT && has_add) tc2_epilogue_tile_add<DBG, true, true>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_BCL_SPLIT) tc2_epilogue_tile<OUT_BCL_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_BCL && has_add && a.res_split) tc2_epilogue_tile_add<DBG, true, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_BCL && has_add) tc2_epilogue_tile_add<DBG, false, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else if (a.out_layout == OUT_PHASE_SPLIT) tc2_epilogue_tile<OUT_PHASE_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
-      else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups);
+      auto run_epi = [&](int m0, int m1) {
+        if (a.out_layout == OUT_BCL_SPLIT && has_add) tc2_epilogue_tile_add<DBG, true, true>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_BCL_SPLIT) tc2_epilogue_tile<OUT_BCL_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_BCL && has_add && a.res_split) tc2_epilogue_tile_add<DBG, true, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_BCL && has_add) tc2_epilogue_tile_add<DBG, false, false>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_BCL) tc2_epilogue_tile<OUT_BCL, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_BLC) tc2_epilogue_tile<OUT_BLC, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else if (a.out_layout == OUT_PHASE_SPLIT) tc2_epilogue_tile<OUT_PHASE_SPLIT, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+        else tc2_epilogue_tile<OUT_PHASE, DBG>(p, acc, q, lane, b, t0, nt, wa, grp, epi_groups, m0, m1);
+      };
+      if (p.acc_per_mt) {   // M tile by M tile: each tile's issuer restarts while the next tile is still being drained
+        for (int m = 0; m < p.m_tiles; ++m) {
+          run_epi(m, m + 1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(32 + as * 4 + m));
+        }
+        continue;
+      }
+      run_epi(0, p.m_tiles);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(6 + as));
@@ -1221,7 +1243,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) conv_tc2_kernel(const Tc2Args 
 inline size_t tc2_smem_bytes(const Tc2Args& p) {
   const size_t a_bytes = (size_t)p.rows_alloc * p.ck * 2;
   const size_t w_bytes = p.w_resident ? (size_t)p.kblocks * p.NT * 64 : (size_t)p.w_stages * p.stage_bytes;
-  return p.a_stages * 2 * a_bytes + w_bytes + 33 * 8;
+  return p.a_stages * 2 * a_bytes + w_bytes + 41 * 8;
 }
 
 // Choose tile shape / buffering for one layer launch.  Preference order: weights resident in smem (no L2
@@ -1384,6 +1406,10 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   int cols = 32;
   while (cols < p.acc_stages * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
+  // measured (gpurun r2r): the issuers drift apart by half an epilogue and hold the shared weight-ring slots longer — Basis-MelGAN
+  // 11.2 -> 11.8-12.0 ms, MelGAN 16.9 -> 17.3 -> opt-in only
+  static const int per_mt_env = getenv("FV_TC2_ACC_PER_MT") ? atoi(getenv("FV_TC2_ACC_PER_MT")) : 0;
+  p.acc_per_mt = (per_mt_env && p.acc_stages == 1 && p.m_tiles == p.n_issuers && p.m_tiles <= 4 && p.m_tiles > 1) ? 1 : 0;
   p.idesc = make_idesc_f16(128, NT);
   p.idesc2 = make_idesc_f16(128, 2 * NT);
   p.tiles_per_batch = (a.Lpos + best.mt * 128 - 1) / (best.mt * 128);
@@ -1606,6 +1632,7 @@ struct Tc3Args {
   float inv_slope;         // 1 / slope (slope > 0): undoes the LeakyReLU baked into the split copy
   int x_rows_alloc;        // row stride of the A1 planes (x_rows rounded up to 8 in split mode: 128-B aligned TMA boxes)
   int epi_groups;          // split mode: 1 or 2 warps per TMEM lane quarter in each of epiA / epiB
+  int pair_issue;          // resident, non-ping-pong plans with one M tile per issuer: conv1(i+1) and conv2(i) issued interleaved
   // Streamed weights (the two images do not fit next to the tiles: C = 64, k = 7 / 11): warp 11 feeds a ring of
   // `w_stages` slots, one slot = one tap (ksteps k-blocks = stage_bytes), in the order the issuers consume them
   // (conv1 of tile 0, then per tile conv2(i), conv1(i+1)).  Resident mode: w_resident = 1.
@@ -1636,6 +1663,26 @@ __device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_
 }
 
 enum { IO_F32 = 0, IO_SPLIT_SPLIT = 1, IO_SPLIT_F32 = 2 };
+
+// conv1 of the NEXT tile and conv2 of the current one are independent (different A buffers, weights, accumulators): issued
+// interleaved, tap by tap, an issuer that owns one M tile drives TWO accumulator chains instead of one, i.e. each dependent
+// UMMA waits for half as long (k = 3 units are bound by exactly that chain latency).
+template <int KS>
+__device__ __forceinline__ void issue_conv_pair_1mt(uint64_t ad1, uint64_t bd1, uint32_t d1, uint64_t tap1_16, uint64_t ks1_16,
+                                                    uint64_t lo1_16, uint64_t ad2, uint64_t bd2, uint32_t d2, uint64_t ks2_16,
+                                                    uint64_t lo2_16, int K, uint64_t kb_step16, uint32_t idesc, uint32_t idesc2) {
+  uint32_t accum = 0u;
+  for (int j = 0; j < K; ++j, ad1 += tap1_16, ad2 += 1, bd1 += KS * kb_step16, bd2 += KS * kb_step16) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      umma_f16_elect(d1, ad1 + ks * ks1_16, bd1 + ks * kb_step16, idesc2, accum);
+      umma_f16_elect(d2, ad2 + ks * ks2_16, bd2 + ks * kb_step16, idesc2, accum);
+      umma_f16_elect(d1, ad1 + ks * ks1_16 + lo1_16, bd1 + ks * kb_step16, idesc, 1u);
+      umma_f16_elect(d2, ad2 + ks * ks2_16 + lo2_16, bd2 + ks * kb_step16, idesc, 1u);
+      accum = 1u;
+    }
+  }
+}
 
 template <bool DBG, int IO>
 __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc3Args p, const __grid_constant__ CUtensorMap tm_main,
@@ -1958,6 +2005,31 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           umma_commit_elect(BAR(9));
           umma_commit_elect(BAR(10 + bs));
         };
+        // conv1(i + 1) and conv2(i) interleaved (issue_conv_pair_1mt): resident weights, one M tile per issuer, no ping-pong
+        auto conv_pair = [&](int i1, int i2) {
+          const int s = i1 % p.a1_stages, as = i1 % p.acc1_stages, bs = i2 % p.acc2_stages;
+          wa.wait(1, BAR(0 + s), (uint32_t)((i1 / p.a1_stages) & 1), 820 + s);
+          if (i1 >= p.acc1_stages) wa.wait(2, BAR(6 + as), (uint32_t)((i1 / p.acc1_stages - 1) & 1), 830 + as);
+          wa.wait(3, BAR(8), (uint32_t)(i2 & 1), 840);
+          if (i2 >= p.acc2_stages) wa.wait(4, BAR(12 + bs), (uint32_t)((i2 / p.acc2_stages - 1) & 1), 850 + bs);
+          tc_fence_after();
+          const uint64_t ad1 = a1_tmpl + (uint64_t)((smem_u32(A1 + (size_t)s * 2 * a1_bytes) >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
+          const uint64_t ad2 = a2_tmpl + (uint64_t)((smem_u32(A2) >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
+          const uint64_t bd1 = b_tmpl + (uint64_t)((w1s >> 4) & 0x3FFF), bd2 = b_tmpl + (uint64_t)((w2s >> 4) & 0x3FFF);
+          const uint32_t d1 = tmem_base + (uint32_t)(as * p.acc_cols) + (uint32_t)wid * mt_cols;
+          const uint32_t d2 = acc2_base + (uint32_t)(bs * p.acc_cols) + (uint32_t)wid * mt_cols;
+          const uint64_t ks1 = 2ull * (uint64_t)p.x_rows_alloc, ks2 = 2ull * (uint64_t)p.h_rows_alloc;
+          const uint64_t lo1 = (uint64_t)(a1_bytes >> 4), lo2 = (uint64_t)(a2_bytes >> 4);
+          if (ksteps == 1) issue_conv_pair_1mt<1>(ad1, bd1, d1, (uint64_t)p.dil, ks1, lo1, ad2, bd2, d2, ks2, lo2, K, kb_step16, idesc, idesc2);
+          else if (ksteps == 2) issue_conv_pair_1mt<2>(ad1, bd1, d1, (uint64_t)p.dil, ks1, lo1, ad2, bd2, d2, ks2, lo2, K, kb_step16, idesc, idesc2);
+          else issue_conv_pair_1mt<4>(ad1, bd1, d1, (uint64_t)p.dil, ks1, lo1, ad2, bd2, d2, ks2, lo2, K, kb_step16, idesc, idesc2);
+          umma_commit_elect(BAR(2 + s));
+          umma_commit_elect(BAR(4 + as));
+          umma_commit_elect(BAR(9));
+          umma_commit_elect(BAR(10 + bs));
+        };
+        const bool pair_issue = p.pair_issue && !p.pp && p.w_resident && p.a1_stages == 2 && m_tiles <= n_iss &&
+                                (ksteps == 1 || ksteps == 2 || ksteps == 4);
         if (p.pp) {
           for (int i = 0; i < n_my; i += 2) {
             conv1(i);
@@ -1966,6 +2038,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             if (i + 1 < n_my) conv2(i + 1);
           }
         } else if (n_my > 0) conv1(0);
+        if (pair_issue) {
+          for (int i = 0; i < n_my; ++i) {
+            if (i + 1 < n_my) conv_pair(i + 1, i);
+            else conv2(i);
+          }
+        } else
         for (int i = 0; i < n_my && !p.pp; ++i) {
           if (conv2_first) {
             conv2(i);
@@ -2361,6 +2439,10 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
   p.inv_slope = slope > 0.f ? 1.0f / slope : 1.0f;
   static const int epi_env = getenv("FV_TC3_EPI") ? atoi(getenv("FV_TC3_EPI")) : 2;   // epilogue warp groups in split mode
   p.epi_groups = (io != IO_F32 && epi_env >= 2) ? 2 : 1;
+  // measured (gpurun r2q): the interleaved pair must wait for epiA(i) AND the load of tile i+1 before either conv starts,
+  // which costs more than the second accumulator chain gains (C=64 k=3 units +8..+20 %) -> opt-in only
+  static const int pair_env = getenv("FV_TC3_PAIR") ? atoi(getenv("FV_TC3_PAIR")) : 0;
+  p.pair_issue = pair_env ? 1 : 0;
   p.w1img = l1.image; p.w2img = l2.image;
   p.slope = slope; p.acc_mode = acc_mode; p.acc_div = acc_div;
   CUtensorMap tm_main, tm_tail;
