@@ -1058,8 +1058,8 @@ int fv_encode_16bits(const float* x, int64_t n, float rescale_out, int16_t* out,
   if (!x || !out || !scratch1 || n <= 0) return fail(FV_EINVAL, "fv_encode_16bits: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   FV_CUDA(cudaMemsetAsync(scratch1, 0, sizeof(float), st));
-  absmax_kernel<<<grid_for(n), 256, 0, st>>>(x, n, (unsigned int*)scratch1);
-  encode16_kernel<<<grid_for(n), 256, 0, st>>>(x, n, (const unsigned int*)scratch1, rescale_out, (short*)out);
+  absmax_kernel<<<grid_for((n + 3) / 4), 256, 0, st>>>(x, n, (unsigned int*)scratch1);
+  encode16_kernel<<<grid_for((n + 3) / 4), 256, 0, st>>>(x, n, (const unsigned int*)scratch1, rescale_out, (short*)out);
   g_launches += 2;
   FV_CUDA(cudaGetLastError());
   return FV_OK;

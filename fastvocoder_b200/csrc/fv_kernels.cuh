@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 
 namespace fv {
 
@@ -321,9 +322,11 @@ inline bool conv_narrow_v4_ok(const ConvArgs& a) {
 // produces 4 consecutive positions from three aligned 16-byte loads per input channel (window t0-4 .. t0+7, all indices
 // compile-time -> registers), the 7*NOUT weights of the channel come from shared memory as broadcast 16-byte reads, and
 // tiles that touch the padding / the ragged end take the scalar path of conv_narrow_kernel's arithmetic.
-template <int NOUT>
+// Q = quads (4 outputs) per thread: Q = 2 loads 4 aligned float4 per channel for 8 outputs (2x instead of 3x re-reads through
+// L1, 14 instead of 2 x 10 activations) — same per-output FMA order, so Q = 1 and Q = 2 are bit-identical.
+template <int NOUT, int Q>
 __global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
-  constexpr int K = 7, PADL = 3;
+  constexpr int K = 7, PADL = 3, T = 4 * Q;
   extern __shared__ __align__(16) float smem[];   // [Cin][NOUT][8] (tap 7 = 0)
   for (int i = threadIdx.x; i < a.Cin * NOUT * 8; i += blockDim.x) {
     const int j = i & 7, n = (i >> 3) % NOUT, ci = i / (8 * NOUT);
@@ -334,25 +337,29 @@ __global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
   const float* __restrict__ xb = a.x + (long long)b * a.x_bs;
   float* __restrict__ yb = a.y + (long long)b * a.y_bs;
   const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;
-  const int nquads = (a.Lpos + 3) >> 2;
+  const int ngroups = (a.Lpos + T - 1) / T;
   const float slope = a.pre_slope;
   const uint32_t uL = (uint32_t)a.Lin;
-  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < nquads; qd += gridDim.x * blockDim.x) {
-    const int t0 = qd << 2;
-    float acc[NOUT][4];
+  for (int qd = blockIdx.x * blockDim.x + threadIdx.x; qd < ngroups; qd += gridDim.x * blockDim.x) {
+    const int t0 = qd * T;
+    float acc[NOUT][T];
 #pragma unroll
     for (int n = 0; n < NOUT; ++n)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[n][q] = 0.f;
-    if (t0 - 4 >= 0 && t0 + 8 <= Lb && t0 + 4 <= a.Lpos) {   // interior: the whole 12-sample window is real data
+      for (int q = 0; q < T; ++q) acc[n][q] = 0.f;
+    if (t0 - 4 >= 0 && t0 + T + 4 <= Lb && t0 + T <= a.Lpos) {   // interior: the whole (T + 8)-sample window is real data
       const float* px = xb + t0;
 #pragma unroll 2
       for (int ci = 0; ci < a.Cin; ++ci) {
         const float4* xr = reinterpret_cast<const float4*>(px + (uint32_t)ci * uL);
-        const float4 v0 = __ldg(xr - 1), v1 = __ldg(xr), v2 = __ldg(xr + 1);
-        float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        float w[T + 8];
 #pragma unroll
-        for (int i = 1; i < 11; ++i) w[i] = pre_act(w[i], slope);   // w[0], w[11] are never used (window t0-3 .. t0+6)
+        for (int v = 0; v < Q + 2; ++v) {
+          const float4 f = __ldg(xr + (v - 1));
+          w[4 * v] = f.x; w[4 * v + 1] = f.y; w[4 * v + 2] = f.z; w[4 * v + 3] = f.w;
+        }
+#pragma unroll
+        for (int i = 1; i < T + 7; ++i) w[i] = pre_act(w[i], slope);   // w[0], w[T+7] are never used (window t0-3 .. t0+T+2)
 #pragma unroll
         for (int n = 0; n < NOUT; ++n) {
           const float4 c0 = *reinterpret_cast<const float4*>(smem + (ci * NOUT + n) * 8);
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
 #pragma unroll
           for (int j = 0; j < K; ++j)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[n][q] = fmaf(cw[j], w[q + j + (4 - PADL)], acc[n][q]);
+            for (int q = 0; q < T; ++q) acc[n][q] = fmaf(cw[j], w[q + j + (4 - PADL)], acc[n][q]);
         }
       }
     } else {   // padding / ragged end / tail: scalar taps with the generic index rules
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
         const float* xr = xb + (long long)ci * a.Lin;
         for (int j = 0; j < K; ++j) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < T; ++q) {
             int g = t0 + q - PADL + j;
             if (a.pad_mode == PAD_REFLECT) {
               if (g < 0) g = -g;
@@ -386,17 +393,20 @@ __global__ void __launch_bounds__(256) conv_narrow7_kernel(const ConvArgs a) {
     for (int n = 0; n < NOUT; ++n) {
       if (n >= a.N) break;
       const float bv = a.bias ? __ldg(a.bias + n) : 0.f;
-      float o[4];
+      float o[T];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < T; ++q) {
         o[q] = acc[n][q] + bv;
         if (a.post_tanh) o[q] = tanhf(o[q]);
       }
       float* yo = yb + (long long)n * a.Lpos + t0;
-      if (t0 + 4 <= a.Lpos) {
-        *reinterpret_cast<float4*>(yo) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
-        for (int q = 0; q < 4 && t0 + q < a.Lpos; ++q) yo[q] = o[q];
+#pragma unroll
+      for (int v = 0; v < Q; ++v) {
+        if (t0 + 4 * v + 4 <= a.Lpos) {
+          *reinterpret_cast<float4*>(yo + 4 * v) = make_float4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+        } else {
+          for (int q = 4 * v; q < 4 * v + 4 && t0 + q < a.Lpos; ++q) yo[q] = o[q];
+        }
       }
     }
   }
@@ -410,13 +420,18 @@ inline bool conv_narrow7_ok(const ConvArgs& a) {
          (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0;
 }
 inline cudaError_t launch_conv_narrow7(const ConvArgs& a, cudaStream_t st) {
-  long long g4 = ((a.Lpos + 3) / 4 + 255) / 256;
+  // outputs per thread / 4 (single-channel output).  Measured (gpurun r2s): Q = 2 is SLOWER (conv_post 0.148 -> 0.160 ms, MelGAN
+  // LastLayer 0.271 -> 0.320 ms: half the threads, fewer loads in flight) -> Q = 1 stays the default
+  static const int q_env = getenv("FV_NARROW7_Q") ? atoi(getenv("FV_NARROW7_Q")) : 1;
+  const int Qn = (a.N == 1 && q_env >= 2) ? 2 : 1;
+  long long g4 = ((a.Lpos + 4 * Qn - 1) / (4 * Qn) + 255) / 256;
   if (g4 > 148 * 16) g4 = 148 * 16;
   if (g4 < 1) g4 = 1;
   dim3 grid((unsigned)g4, a.B);
-  if (a.N == 1) conv_narrow7_kernel<1><<<grid, 256, (size_t)a.Cin * 1 * 8 * sizeof(float), st>>>(a);
-  else if (a.N == 2) conv_narrow7_kernel<2><<<grid, 256, (size_t)a.Cin * 2 * 8 * sizeof(float), st>>>(a);
-  else conv_narrow7_kernel<4><<<grid, 256, (size_t)a.Cin * 4 * 8 * sizeof(float), st>>>(a);
+  if (a.N == 1 && Qn == 2) conv_narrow7_kernel<1, 2><<<grid, 256, (size_t)a.Cin * 1 * 8 * sizeof(float), st>>>(a);
+  else if (a.N == 1) conv_narrow7_kernel<1, 1><<<grid, 256, (size_t)a.Cin * 1 * 8 * sizeof(float), st>>>(a);
+  else if (a.N == 2) conv_narrow7_kernel<2, 1><<<grid, 256, (size_t)a.Cin * 2 * 8 * sizeof(float), st>>>(a);
+  else conv_narrow7_kernel<4, 1><<<grid, 256, (size_t)a.Cin * 4 * 8 * sizeof(float), st>>>(a);
   g_launches++;
   return cudaGetLastError();
 }
@@ -864,10 +879,30 @@ __global__ void relu_transpose_sub_kernel(const float* __restrict__ x, const flo
 }
 
 // save_wav quantiser (data/audio.py:12-14): peak -> scale -> int16 truncation
+// Both passes are HBM streams: 16-byte loads (8-byte int16 stores), four independent vectors in flight per thread; the scalar
+// loops take unaligned buffers and the tail.  Same arithmetic per element as the scalar form (max / one fp32 multiply + truncation).
 __global__ void absmax_kernel(const float* __restrict__ x, long long n, unsigned int* __restrict__ out_bits) {
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(x[i]));
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  long long done = 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = n >> 2;
+    long long i = tid;
+    for (; i + 3 * nth < n4; i += 4 * nth) {
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + nth), c = __ldg(x4 + i + 2 * nth), d = __ldg(x4 + i + 3 * nth);
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
+                         fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    }
+    for (; i < n4; i += nth) {
+      const float4 a = __ldg(x4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += nth) m = fmaxf(m, fabsf(x[i]));
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out_bits, __float_as_uint(m));  // non-negative floats order like uints
@@ -877,8 +912,24 @@ __global__ void encode16_kernel(const float* __restrict__ x, long long n, const 
   // numpy: x *= 32767 / max(0.01, max|x|) * rescale_out  (python float64 scalar, applied to a float32 array)
   const double scale = 32767.0 / fmax(0.01, (double)__uint_as_float(*peak_bits)) * (double)rescale;
   const float s = (float)scale;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = (short)(int)(x[i] * s);  // astype(int16): truncation toward zero
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  long long done = 0;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    short4* o4 = reinterpret_cast<short4*>(out);
+    const long long n4 = n >> 2;
+    auto q = [s](const float4& v) {   // astype(int16): truncation toward zero
+      return make_short4((short)(int)(v.x * s), (short)(int)(v.y * s), (short)(int)(v.z * s), (short)(int)(v.w * s));
+    };
+    long long i = tid;
+    for (; i + 3 * nth < n4; i += 4 * nth) {
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + nth), c = __ldg(x4 + i + 2 * nth), d = __ldg(x4 + i + 3 * nth);
+      o4[i] = q(a); o4[i + nth] = q(b); o4[i + 2 * nth] = q(c); o4[i + 3 * nth] = q(d);
+    }
+    for (; i < n4; i += nth) o4[i] = q(__ldg(x4 + i));
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += nth) out[i] = (short)(int)(x[i] * s);
 }
 
 }  // namespace fv

@@ -22,7 +22,7 @@ B="python bench.py --steps 1 --warmup 3 --skip-cpu-baseline --headline-only"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $B > $OUT/ncu_launch_$TAG.log 2>&1
 # gpurun merges at most 64 MiB back: every capture is reduced ON THE BOX to its raw-page csv + the text summary; the .ncu-rep
 # itself is kept for the three kernels DESIGN.md discusses (no --import-source: the SASS listings are committed separately)
-KEEP="fused_c32k7 tc2_c128k11 narrow7"
+KEEP="fused_c32k7"
 cap() { # name, kernel regex, skip, extra bench args...
   n=$1; k=$2; s=$3; shift 3
   timeout 600 ncu --set full --clock-control none -k regex:$k -s $s -c 1 -o $OUT/ncu_${n}_$TAG $B "$@" > $OUT/ncu_${n}_$TAG.log 2>&1
@@ -51,4 +51,6 @@ for m in ("hifigan","basis-melgan","multiband-hifigan","melgan","hifigan_fp32pat
     except Exception as e:
         print(m, "failed", e)
 PY
+# gpurun merges at most 64 MiB back: never exceed it
+if [ $(du -sm $OUT | cut -f1) -gt 55 ]; then rm -f $OUT/*.ncu-rep; fi
 ls -la $OUT/*_$TAG.ncu-rep $OUT/*_$TAG.raw.csv; du -sh $OUT
