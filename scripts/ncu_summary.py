@@ -13,7 +13,7 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum",
-        "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.pct", "smsp__sass_average_data_bytes_per_sector_mem_global_op_st.pct",
+        "smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.ratio", "smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio",
         "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio",
         "l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio",
         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
