@@ -6,6 +6,7 @@ a C ABI (include/fastvocoder_b200.h).  No CPU fallback.
 """
 from .generators import (BasisMelGANGenerator, HiFiGANGenerator, MelGANGenerator,  # noqa: F401
                          MultiBandHiFiGANGenerator, build_generator)
+from .pipeline import HostPipeline  # noqa: F401
 from .pqmf import PQMF  # noqa: F401
 
 __version__ = "0.1.0"

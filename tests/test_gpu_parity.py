@@ -706,3 +706,21 @@ def test_rtf_loop_runs_and_reports(tmp_path, specs, capsys):
     assert "duration is 1.05s." in out and "rtf is" in out
     rtf = float(out.strip().splitlines()[-1].split("rtf is")[1].strip().rstrip("."))
     assert 0 < rtf < 1.0
+
+
+def test_host_pipeline_matches_direct_forward(specs):
+    """HostPipeline (H2D / compute / D2H on three streams, double-buffered): every batch's host result equals model(x)."""
+    from fastvocoder_b200.pipeline import HostPipeline
+    for key in ("hifigan-light", "multiband-hifigan-light"):
+        m = make_model(specs, key)
+        fwd = (lambda x: m(x, synthesize=True)[1]) if key.startswith("multiband") else None
+        mels = [torch.from_numpy(synth_mel(3, 64, seed=s)).pin_memory() for s in range(5)]
+        with torch.no_grad():
+            want = [(fwd(x.cuda()) if fwd else m(x.cuda())).cpu() for x in mels]
+        outs = [torch.empty(w.shape).pin_memory() for w in want]
+        pipe = HostPipeline(m, fwd=fwd)
+        for x, o in zip(mels, outs):
+            pipe.submit(x, o)
+        pipe.finish()
+        for w, o in zip(want, outs):
+            assert torch.equal(w, o)
