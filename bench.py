@@ -388,6 +388,8 @@ def roofline_of(ctx, name, model, mel_dev, B, T, label, profile_out=""):
     kernel_names = {"tcgen05": "conv_tc2_kernel (tcgen05, split-fp16 x3, persistent warp-specialised)",
                     "tcgen05-fused-unit": "conv_tc3_fused_kernel (tcgen05 fused ResBlock1 unit: conv1+lrelu+conv2+residual, "
                                           "TMA-fed split fp16 hi/lo activations)",
+                    "tcgen05-fused-stack": "conv_tc3_fused_kernel<IO_STACK> (tcgen05 fused ResidualStack: dilated conv + lrelu + "
+                                           "[1x1 | skip 1x1] pair, h kept in shared memory)",
                     "ffma": "conv_ffma_kernel (fp32 CUDA cores)"}
     achieved_tf = d["flops"] / (d["ms"] * 1e-3) / 1e12
     peak_tf = peaks["tensor_tflops_sustained"]           # kernel timed inside a long step -> sustained figure

@@ -201,8 +201,12 @@ static int run_layer(const Layer& l, const float* wd, const float* bias, const T
     if (rc == 0 && used_tc) *used_tc = 1;
     return rc == 0 ? FV_OK : FV_NOT_APPLICABLE;
   }
-  if (narrow7_env && conv_narrow7_ok(a) && (a.N <= 2 || !(c.allow_tc && !tc_disabled && tcl && tcl->eligible))) {
-    FV_CUDA(launch_conv_narrow7(a, st));
+  // FV_NARROW7_MB=1: also the 64 -> 4 conv_post of Multiband-HiFi-GAN on the staged streaming kernel instead of tcgen05 (A/B)
+  static const bool narrow7_mb_env = getenv("FV_NARROW7_MB") != nullptr && atoi(getenv("FV_NARROW7_MB")) != 0;
+  if (narrow7_env && conv_narrow7_ok(a) &&
+      (a.N <= 2 || (narrow7_mb_env && conv_narrow7_staged_ok(a)) || !(c.allow_tc && !tc_disabled && tcl && tcl->eligible))) {
+    if (conv_narrow7_staged_ok(a)) FV_CUDA(launch_conv_narrow7_staged(a, st));   // bulk-copy staged streaming form (long rows)
+    else FV_CUDA(launch_conv_narrow7(a, st));
     return FV_OK;
   }
   if (c.allow_tc && !tc_disabled && tcl && tcl->eligible && padded_ok) {
@@ -302,7 +306,8 @@ static int eff_batch(const Model& m, int B, int flags) {
 
 struct Profiler {
   struct Rec {
-    int layer, used_tc;   // used_tc: 0 fp32 conv, 1 tcgen05 conv, 2 tcgen05 fused ResBlock1 unit (layer = conv1, + conv2)
+    int layer, used_tc;   // used_tc: 0 fp32 conv, 1 tcgen05 conv, 2 tcgen05 fused ResBlock1 unit (layer = conv1, + conv2),
+                          // 3 tcgen05 fused ResidualStack (layer = the dilated conv, + the 1x1 pair)
     long long Lin;
     int B;
     cudaEvent_t e0, e1;
@@ -617,6 +622,32 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
           static const bool stack_split_env = getenv("FV_STACK_SPLIT") == nullptr || atoi(getenv("FV_STACK_SPLIT")) != 0;
           const bool h_split = pair_ok && tc_ok && split_env0 && stack_split_env && !lens_dev && tc3_split_available() &&
                                tc2_stack_split_ok(m, sk, tcl(sk.dil_conv), sk.pair >= 0 ? tcl(sk.pair) : nullptr, nb, Lout, mslope);
+          // One launch for the whole stack where the fused kernel takes it (C <= 64): h stays in shared memory, c is read once
+          // (these stacks are HBM-bound as two launches: 640 B -> 256 B per position at C = 32).  FV_STACK_FUSED=0: off.
+          static const bool stack_fused_env = getenv("FV_STACK_FUSED") == nullptr || atoi(getenv("FV_STACK_FUSED")) != 0;
+          if (pair_ok && tc_ok && fuse_ok && stack_fused_env && sk.pair >= 0) {
+            const Layer& d = m.layers[sk.dil_conv];
+            const TcLayer* td = tcl(sk.dil_conv);
+            const TcLayer* tp = tcl(sk.pair);
+            const int pad = (d.K - 1) * d.dil / 2;
+            if (td && tp && !d.causal && d.Cin == d.Cout && m.layers[sk.pair].Cout == d.Cout && m.layers[sk.pair].Cin == 2 * d.Cout) {
+              if (pad >= Lout) return fail(FV_EINVAL, "ReflectionPad1d needs pad (%d) < length (%lld)", pad, Lout);
+              Profiler::Rec r{};
+              if (prof) {
+                r.layer = sk.dil_conv; r.Lin = Lout; r.B = nb; r.used_tc = 3;
+                cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+                cudaEventRecord(r.e0, st);
+              }
+              const int frc = launch_fused_stack(sc_in, dst, bias(sk.dil_conv), bias(sk.pair), *td, *tp, nb, d.Cout, (int)Lout,
+                                                 d.K, d.dil, mslope, true, st, sl);
+              if (prof) {
+                if (frc == 0) { cudaEventRecord(r.e1, st); prof->recs.push_back(r); }
+                else { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+              }
+              if (frc < 0) return fail(FV_ECUDA, "fused stack launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+              if (frc == 0) { sc_in = dst; continue; }
+            }
+          }
           LayerCall l1;
           l1.x = sc_in; l1.y = bufH; l1.B = nb; l1.Lin = Lout; l1.pre_slope = mslope; l1.pad_mode = PAD_REFLECT; l1.lens = sl;
           l1.out_split = h_split; l1.out_slope = mslope;
@@ -878,6 +909,7 @@ int fv_forward_profile(fv_handle* h, const float* mel, int B, int T, float* out,
       o.positions = (int64_t)r.B * r.Lin;
       // algorithmic MACs: every input sample meets every (Cout, tap) of the reference op
       o.flops = 2.0 * (double)l.Cin * l.Cout * l.K * (double)r.Lin * r.B * (r.used_tc == 2 ? 2.0 : 1.0);
+      if (r.used_tc == 3) o.flops += 2.0 * 2.0 * (double)l.Cout * l.Cout * (double)r.Lin * r.B;   // + stack.4 and skip_layer (1x1)
       // algorithmic HBM bytes if nothing were cached: read x, write y (+ read residual for half the convs, ignored)
       o.bytes = 4.0 * r.B * ((double)l.Cin * r.Lin + (double)l.Cout * (double)layer_out_len(l, r.Lin) /
                                                          (l.type == L_BASIS ? l.Cout : 1));
@@ -994,6 +1026,32 @@ int fv_residual_stack(const float* c, const float* w_dil, const float* b_dil, co
   float* hbuf = scratch;
   float* ubuf = scratch + (size_t)B * C * L;
   Layer ld = make_conv_layer(C, C, K, dilation);
+  if (use_tc >= 2) {   // fused ResidualStack kernel (one launch); falls through to the layer-by-layer path when not applicable
+    if (B <= 0 || C <= 0 || L <= 0 || K <= 0 || K % 2 == 0 || dilation <= 0) return fail(FV_EINVAL, "fv_residual_stack: bad argument");
+    if ((K - 1) * dilation / 2 >= L) return fail(FV_EINVAL, "ReflectionPad1d needs pad (%d) < length (%d)", (K - 1) * dilation / 2, L);
+    Layer lp;
+    lp.type = L_PAIR; lp.Cin = 2 * C; lp.Cout = C; lp.K = 1; lp.dil = 1; lp.N = C; lp.Kd = 1;
+    const size_t n1 = ((size_t)C * K * C + 63) / 64 * 64, n2 = ((size_t)2 * C * C + 63) / 64 * 64;
+    float* both = nullptr;
+    FV_CUDA(cudaMalloc(&both, (n1 + n2 + 64 + (size_t)C) * sizeof(float)));
+    std::vector<Layer> two{ld, lp};
+    two[0].wd_offset = 0;
+    two[1].wd_offset = (int64_t)n1;
+    int rc = derive_layer(ld, w_dil, both, st);
+    if (!rc) rc = derive_pair(lp, w_1x1, w_skip, b_1x1, b_skip, both + n1, st);
+    TcWeights tcw;
+    int frc = 1;
+    if (!rc && tcw.build(two, both, st) == 0 && tcw.layer(0) && tcw.layer(1))
+      frc = launch_fused_stack(c, y, b_dil, pair_bias_ptr(lp, both + n1), *tcw.layer(0), *tcw.layer(1), B, C, L, K, dilation, 0.2f,
+                               true, st);
+    cudaError_t se = cudaStreamSynchronize(st);
+    cudaFree(both);
+    tcw.release();
+    if (rc) return rc;
+    if (frc < 0 || se != cudaSuccess) return fail(FV_ECUDA, "fused stack failed: %s", cudaGetErrorString(se));
+    if (frc == 0) return FV_OK;
+    if (use_tc == 3) return fail(FV_EINVAL, "fv_residual_stack: shape not handled by the fused stack kernel");
+  }
   LayerCall c1;
   c1.x = c; c1.y = hbuf; c1.B = B; c1.Lin = L; c1.pre_slope = 0.2f; c1.pad_mode = PAD_REFLECT;
   int rc = conv_raw(ld, w_dil, b_dil, c1, use_tc, st);

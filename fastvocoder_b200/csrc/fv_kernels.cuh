@@ -671,10 +671,96 @@ __global__ void __launch_bounds__(256) pqmf_synthesis_poly_kernel(const float* _
     }
   }
 }
+// 256-bit global store (sm_100: STG.E.ENL2.256): eight consecutive floats of one thread in one fully used 32-byte sector
+__device__ __forceinline__ void st_global_v8(float* p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+// Same polyphase sum with the memory side vectorised: one thread owns G = 4 CONSECUTIVE position groups (16 output samples).
+// Its window of a band is x[k, q0-7 .. q0+11], fetched as five aligned 16-byte loads (the kernel above issues 64 scalar loads
+// per band for the same 4 groups and re-reads every sample 16x through L1), the four coefficients of a (band, window tap)
+// pair — one per output phase r — are ONE 16-byte shared-memory read, and the 16 outputs leave as two 32-byte stores.
+// Per output the products are still added k ascending, then j ascending: bit-identical to both kernels above.
+// Requires Lb % 4 == 0 (16-byte aligned band rows, whole groups) and a 32-byte aligned y.
+template <int S, int NT>
+__global__ void __launch_bounds__(128) pqmf_synthesis_poly_v4_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                                     float* __restrict__ y, int Lb,
+                                                                     const int* __restrict__ lens) {
+  static_assert(S == 4 && NT == 63, "shipped PQMF(subbands=4, taps=62) only");
+  constexpr int P = (NT - 1) / 2;                 // 31
+  constexpr int MLO = -(P / S);                   // -7
+  constexpr int MHI = (NT - 1 + S - 1 - P) / S;   // 8
+  constexpr int W = MHI - MLO + 1;                // 16 window taps per output
+  constexpr int G = 4;                            // position groups per thread
+  __shared__ float4 sh[S * W];                    // [k][w] -> coefficients of phases r = 0..3 (0 where the tap does not exist)
+  for (int i = threadIdx.x; i < S * W; i += blockDim.x) {
+    const int k = i / W, w = i - k * W;
+    float c[S];
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+      const int j = S * (MLO + w) - r + P;
+      c[r] = (j >= 0 && j < NT) ? (float)S * h[k * NT + j] : 0.f;   // (S*x)*h == x*(S*h) exactly: S is a power of two
+    }
+    sh[i] = make_float4(c[0], c[1], c[2], c[3]);
+  }
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int q0 = (blockIdx.x * blockDim.x + threadIdx.x) * G;
+  if (q0 >= Lb) return;
+  const int Lv = lens ? __ldg(lens + b) : Lb;
+  const bool interior = q0 - 8 >= 0 && q0 + 12 <= Lv;
+  float acc[G][S];
+#pragma unroll
+  for (int u = 0; u < G; ++u)
+#pragma unroll
+    for (int r = 0; r < S; ++r) acc[u][r] = 0.f;
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    const float* xk = x + ((long long)b * S + k) * Lb;
+    float xw[20];                                 // x[k, q0 - 8 + i]
+    if (interior) {
+      const float4* xv = reinterpret_cast<const float4*>(xk + q0 - 8);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        const float4 f = __ldg(xv + v);
+        xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 20; ++i) {
+        const int n = q0 - 8 + i;
+        xw[i] = (n >= 0 && n < Lv) ? __ldg(xk + n) : 0.f;   // out-of-range samples contribute an exact 0 * h
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const float4 c = sh[k * W + w];
+      const float cr[S] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int r = 0; r < S; ++r) {
+        if (S * (MLO + w) - r + P >= NT) continue;          // the one (w, r) pair without a tap: skipped, as above (compile time)
+#pragma unroll
+        for (int u = 0; u < G; ++u) acc[u][r] = fmaf(xw[u + w + 1], cr[r], acc[u][r]);   // n = q0 + u + MLO + w
+      }
+    }
+  }
+  float* yo = y + ((long long)b * Lb + q0) * S;
+#pragma unroll
+  for (int u = 0; u < G; u += 2) {
+    const float v[8] = {acc[u][0], acc[u][1], acc[u][2], acc[u][3], acc[u + 1][0], acc[u + 1][1], acc[u + 1][2], acc[u + 1][3]};
+    st_global_v8(yo + u * S, v);
+  }
+}
 // host dispatch: the polyphase kernel for the reference's PQMF(subbands=4, taps=62), the generic kernel otherwise
 inline cudaError_t launch_pqmf_synthesis(const float* x, const float* h, float* y, int B, int S, int taps, int Lb,
                                          const int* lens, cudaStream_t st) {
-  if (S == 4 && taps == 62 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+  static const bool v4_env = getenv("FV_PQMF_V4") == nullptr || atoi(getenv("FV_PQMF_V4")) != 0;   // A/B switch
+  if (v4_env && S == 4 && taps == 62 && Lb % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    dim3 grid((Lb / 4 + 127) / 128, B);
+    pqmf_synthesis_poly_v4_kernel<4, 63><<<grid, 128, 0, st>>>(x, h, y, Lb, lens);
+  } else if (S == 4 && taps == 62 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     constexpr int QT = 4;
     dim3 grid((Lb + 256 * QT - 1) / (256 * QT), B);
     pqmf_synthesis_poly_kernel<4, 63, QT><<<grid, 256, 0, st>>>(x, h, y, Lb, lens);
@@ -768,9 +854,65 @@ __global__ void __launch_bounds__(256) pqmf_analysis_win_kernel(const float* __r
     for (int k = 0; k < S; ++k) y[((long long)b * S + k) * Lb + n] = acc[u][k];
   }
 }
+// Vectorised memory side of the same sum: one thread owns 4 CONSECUTIVE outputs n0..n0+3 of all S bands.  Their inputs are the
+// 75 samples x[4*n0 - 31 .. 4*n0 + 43], fetched as nineteen aligned 16-byte loads (the kernel above: 63 scalar loads per output),
+// each coefficient vector is one 16-byte shared read feeding 16 FMAs, and every band row gets one 16-byte store.
+// Same addition order per output (j ascending) -> identical bits.  Requires L % 4 == 0 and Lb % 4 == 0.
+template <int S, int NT>
+__global__ void __launch_bounds__(128) pqmf_analysis_v4_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                               float* __restrict__ y, int L, int Lb) {
+  static_assert(S == 4 && NT == 63, "shipped PQMF(subbands=4, taps=62) only");
+  constexpr int P = (NT - 1) / 2;
+  constexpr int G = 4;
+  __shared__ float4 sh[NT];   // [j] -> (h[0][j], h[1][j], h[2][j], h[3][j])
+  for (int j = threadIdx.x; j < NT; j += blockDim.x) sh[j] = make_float4(h[j], h[NT + j], h[2 * NT + j], h[3 * NT + j]);
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * G;
+  if (n0 >= Lb) return;
+  const float* xb = x + (long long)b * L;
+  const int g0 = n0 * S - (P + 1);                 // window base: x[g0 + i], i in [0, 76)
+  float xw[76];
+  if (g0 >= 0 && g0 + 76 <= L) {
+    const float4* xv = reinterpret_cast<const float4*>(xb + g0);
+#pragma unroll
+    for (int v = 0; v < 19; ++v) {
+      const float4 f = __ldg(xv + v);
+      xw[4 * v] = f.x; xw[4 * v + 1] = f.y; xw[4 * v + 2] = f.z; xw[4 * v + 3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 76; ++i) {
+      const int g = g0 + i;
+      xw[i] = (g >= 0 && g < L) ? __ldg(xb + g) : 0.f;
+    }
+  }
+  float acc[G][S];
+#pragma unroll
+  for (int u = 0; u < G; ++u)
+#pragma unroll
+    for (int k = 0; k < S; ++k) acc[u][k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const float4 c4 = sh[j];
+    const float c[S] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int u = 0; u < G; ++u)
+#pragma unroll
+      for (int k = 0; k < S; ++k) acc[u][k] = fmaf(xw[S * u + j + 1], c[k], acc[u][k]);   // x index 4(n0+u) + j - P
+  }
+#pragma unroll
+  for (int k = 0; k < S; ++k)
+    *reinterpret_cast<float4*>(y + ((long long)b * S + k) * Lb + n0) = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+}
 inline cudaError_t launch_pqmf_analysis(const float* x, const float* h, float* y, int B, int S, int taps, long long L,
                                         long long Lb, cudaStream_t st) {
-  if (S == 4 && taps == 62 && L < 0x7fffffffLL) {
+  static const bool v4_env = getenv("FV_PQMF_V4") == nullptr || atoi(getenv("FV_PQMF_V4")) != 0;   // A/B switch
+  if (v4_env && S == 4 && taps == 62 && L < 0x7fffffffLL && L % 4 == 0 && Lb % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    dim3 grid((unsigned)((Lb / 4 + 127) / 128), B);
+    pqmf_analysis_v4_kernel<4, 63><<<grid, 128, 0, st>>>(x, h, y, (int)L, (int)Lb);
+  } else if (S == 4 && taps == 62 && L < 0x7fffffffLL) {
     constexpr int QT = 4;
     dim3 grid((unsigned)((Lb + 256 * QT - 1) / (256 * QT)), B);
     pqmf_analysis_win_kernel<4, 63, QT><<<grid, 256, 0, st>>>(x, h, y, (int)L, (int)Lb);

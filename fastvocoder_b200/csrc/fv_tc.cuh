@@ -332,10 +332,13 @@ constexpr int LD_MAX = 5;
 // elements): one IMAD.WIDE per global address instead of a chain of 64-bit multiplies and adds — these kernels are
 // bound by the instruction stream of their loader / epilogue warps (ncu: 60-65 % issue-slot utilisation, of which the
 // address arithmetic was the largest part).
-template <bool ACT01 = false, class Src>
+// RAW (fused ResidualStack): rows [raw_lo, raw_lo + raw_rows) are ALSO stored un-activated (split hi / lo) at
+// raw_hi / raw_lo_p + (kc * raw_rows + r - raw_lo) * 16 — the same loaded registers feed both copies.
+template <bool ACT01 = false, bool RAW = false, class Src>
 __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, int rows, int nkc, int ltid, int per,
                                                 int rounds, int g0, int Lb, int lstride, bool reflect, Src src,
-                                                int plane_rows = 0) {
+                                                int plane_rows = 0, uint8_t* raw_hi = nullptr, uint8_t* raw_lo_p = nullptr,
+                                                int raw_lo = 0, int raw_rows = 0) {
   if (plane_rows == 0) plane_rows = rows;   // row stride of the 8-channel planes in shared memory (>= rows)
   const int nitems = nkc * rows;
   const uint32_t ls = (uint32_t)lstride;   // unsigned: keeps c * ls a 32-bit multiply feeding one IMAD.WIDE.U32
@@ -346,6 +349,7 @@ __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, in
     float v[LD_MAX][8];
     float sl[LD_MAX];
     int ofs[LD_MAX];
+    int rofs[LD_MAX];
 #pragma unroll
     for (int t = 0; t < LD_MAX; ++t) {
       const bool live = t < per && i0 < nitems;
@@ -362,6 +366,7 @@ __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, in
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[t][c] = ok ? __ldg(pg + (uint32_t)c * ls) : 0.f;
       ofs[t] = live ? (kc * plane_rows + r0) * 16 : -1;
+      if (RAW) rofs[t] = (live && r0 >= raw_lo && r0 < raw_lo + raw_rows) ? (kc * raw_rows + (r0 - raw_lo)) * 16 : -1;
       if (t < per) {   // advance to item i0 + 256
         i0 += 256; kc0 += kstep; r0 += rstep;
         if (r0 >= rows) { r0 -= rows; ++kc0; }
@@ -378,6 +383,12 @@ __device__ __forceinline__ void fill_stage_flat(uint8_t* A_hi, uint8_t* A_lo, in
       }
       *reinterpret_cast<uint4*>(A_hi + ofs[t]) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
       *reinterpret_cast<uint4*>(A_lo + ofs[t]) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      if (RAW && rofs[t] >= 0) {
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) split_f16x2(v[t][c], v[t][c + 1], hp[c >> 1], lp[c >> 1]);
+        *reinterpret_cast<uint4*>(raw_hi + rofs[t]) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        *reinterpret_cast<uint4*>(raw_lo_p + rofs[t]) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      }
     }
   }
 }
@@ -1642,6 +1653,16 @@ struct Tc3Args {
   // in place over the (dead) x tile and conv2 accumulates over the conv1 columns epiA has drained.  Two tiles in flight
   // with half the TMEM / no separate A2 buffer; the issuers walk pairs: conv1(a) conv1(b) conv2(a) conv2(b).
   int pp;
+  // Fused ResidualStack (template parameter IO = IO_STACK, MelGAN family, modules.py:353-382): conv1 = the dilated k-tap conv on
+  // lrelu(c) with reflect padding, conv2 = ONE tap over 2C channels [h | c] with the concatenated image [W_1x1 ; W_skip]
+  // (the stack's 1x1 conv and its skip conv as one GEMM), no residual in epiB.  The loaders put a second, un-activated copy of
+  // the tile's central rows behind the activated planes of the same stage (chunks C/8 .. 2C/8-1, row r = position t0 + r), so
+  // conv2 walks one 2C-channel operand: chunks [0, C/8) = h written in place by epiA, the rest = raw c.  Always ping-pong tiles
+  // with resident weights; h never leaves the SM and c is read once.
+  int stack;
+  int k2, ksteps2, kblocks2;   // conv2: taps, k-steps per tap, k-blocks of its image (HiFi units: K, ksteps, kblocks)
+  int reflect;                 // loaders: ReflectionPad1d instead of zero padding (per utterance length)
+  int ld2_per, ld2_rounds;     // flattened loader plan of the raw copy
   long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
@@ -1650,8 +1671,7 @@ struct Tc3Args {
 template <int KS>
 __device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_t d, int K, uint64_t tap_step16,
                                                uint64_t ks_step16, uint64_t kb_step16, uint64_t lo_delta16,
-                                               uint32_t idesc, uint32_t idesc2) {
-  uint32_t accum = 0u;
+                                               uint32_t idesc, uint32_t idesc2, uint32_t accum = 0u) {
   for (int j = 0; j < K; ++j, ad += tap_step16, bd += KS * kb_step16) {
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -1662,7 +1682,7 @@ __device__ __forceinline__ void issue_conv_1mt(uint64_t ad, uint64_t bd, uint32_
   }
 }
 
-enum { IO_F32 = 0, IO_SPLIT_SPLIT = 1, IO_SPLIT_F32 = 2 };
+enum { IO_F32 = 0, IO_SPLIT_SPLIT = 1, IO_SPLIT_F32 = 2, IO_STACK = 3 };
 
 // conv1 of the NEXT tile and conv2 of the current one are independent (different A buffers, weights, accumulators): issued
 // interleaved, tap by tap, an issuer that owns one M tile drives TWO accumulator chains instead of one, i.e. each dependent
@@ -1689,16 +1709,19 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
                                                                         const __grid_constant__ CUtensorMap tm_tail) {
   extern __shared__ __align__(128) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
+  constexpr bool STK = (IO == IO_STACK);                              // fused ResidualStack (see Tc3Args::stack)
+  constexpr bool SPLIT_IN = (IO == IO_SPLIT_SPLIT || IO == IO_SPLIT_F32);   // x tile fetched by TMA from a split copy
   const int C = p.C, NT = p.C;
-  const uint32_t a1_bytes = (uint32_t)p.x_rows_alloc * C * 2;  // hi or lo of one A1 stage
+  const uint32_t a1_bytes = (uint32_t)(p.x_rows_alloc + (STK ? p.m_out : 0)) * C * 2;  // hi or lo of one A1 stage (STK: + raw planes)
   const uint32_t a2_bytes = (uint32_t)p.h_rows_alloc * C * 2;  // hi or lo of A2
   const int kblock_bytes = NT * 64;
   const uint32_t w_bytes = (uint32_t)p.kblocks * kblock_bytes;
+  const uint32_t w2_bytes = (uint32_t)p.kblocks2 * kblock_bytes;
   uint8_t* A1 = smem;                                            // [a1_stages][hi|lo]
   uint8_t* A2 = A1 + (size_t)p.a1_stages * 2 * a1_bytes;        // [hi|lo]
   uint8_t* W1 = A2 + (p.pp ? 0 : 2 * (size_t)a2_bytes);         // resident: [W1 | W2]; ring: w_stages slots (pp: no A2 buffer)
   uint8_t* W2 = W1 + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(W1 + (p.w_resident ? 2 * (size_t)w_bytes : (size_t)p.w_stages * p.stage_bytes));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(W1 + (p.w_resident ? (size_t)w_bytes + w2_bytes : (size_t)p.w_stages * p.stage_bytes));
   // [0,2) a1_full [2,4) a1_empty [4,6) acc1_full [6,8) acc1_empty  8 a2_full  9 a2_empty  [10,12) acc2_full  [12,14) acc2_empty  14 w_full
   // [15,19) ring slot full  [19,23) ring slot empty
   const uint32_t bar0 = smem_u32(bars);
@@ -1707,8 +1730,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int p2 = (p.K - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
-  const int epi_groups = (IO != IO_F32 && p.epi_groups == 2) ? 2 : 1;
+  const int p2 = (p.k2 - 1) / 2, p1 = (p.K - 1) * p.dil / 2;
+  const int epi_groups = (SPLIT_IN && p.epi_groups == 2) ? 2 : 1;
   // epilogue roles: group 0 = warps 12-15 (epiA) / 16-19 (epiB); split mode with two groups: + warps 0-3 / 4-7
   const bool is_epiA = (warp >= 12 && warp < 16);
   const bool is_epiB = (warp >= 16 && warp < 20) || (epi_groups == 2 && warp >= 4 && warp < 8);
@@ -1718,7 +1741,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(0 + s), IO == IO_F32 ? TC2_LOADER_WARPS : 1);   // split mode: one expect_tx arrive + the TMA bytes
+      mbar_init(BAR(0 + s), SPLIT_IN ? 1 : TC2_LOADER_WARPS);   // split mode: one expect_tx arrive + the TMA bytes
       mbar_init(BAR(2 + s), p.n_issuers);
       mbar_init(BAR(4 + s), p.n_issuers);
       mbar_init(BAR(6 + s), 4 * epiA_groups);
@@ -1775,9 +1798,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       }
       wa.end(p.dbg, 0, lane == 0, it);
   };
-  if (IO != IO_F32 && warp == 0) {
+  if (SPLIT_IN && warp == 0) {
     tma_producer();
-  } else if (IO == IO_F32 && warp < TC2_LOADER_WARPS) {
+  } else if (!SPLIT_IN && warp < TC2_LOADER_WARPS) {
     // ------------------------------------------------------------------ loaders: x tile -> A1[stage]
     const int rows = p.x_rows;
     const int nkc = C >> 3;
@@ -1796,7 +1819,16 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
       const int Lb = p.lens ? __ldg(p.lens + b) : p.L;
       uint8_t* A_hi = A1 + (size_t)s * 2 * a1_bytes;
       uint8_t* A_lo = A_hi + a1_bytes;
-      if (p.ld_per > 0) {
+      if (STK) {   // activated tile (reflect padding) + the un-activated central rows behind it (conv2's skip operand)
+        // (central rows beyond a ragged utterance's end hold reflected samples in both copies: they only feed outputs >= Lb)
+        const float slope1 = p.slope;
+        const uint32_t raw_off = (uint32_t)nkc * (uint32_t)p.x_rows_alloc * 16u;
+        fill_stage_flat<true, true>(A_hi, A_lo, rows, nkc, warp * 32 + lane, p.ld_per, p.ld_rounds, t0 - p2 - p1, Lb, p.L,
+                        p.reflect != 0, [&](int kc, const float*& xc, float& slope) {
+                          xc = xb + (long long)(kc * 8) * p.L;
+                          slope = slope1;
+                        }, p.x_rows_alloc, A_hi + raw_off, A_lo + raw_off, p1, p.m_out);
+      } else if (p.ld_per > 0) {
         const float slope1 = p.slope;
         fill_stage_flat<true>(A_hi, A_lo, rows, nkc, warp * 32 + lane, p.ld_per, p.ld_rounds, t0 - p2 - p1, Lb, p.L,
                         false, [&](int kc, const float*& xc, float& slope) {
@@ -1855,12 +1887,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
     {
       if (wid == TC2_ISSUE_WARPS - 1 && p.w_resident) {
         if (L0) {
-          mbar_expect_tx(BAR(14), 2 * w_bytes);
-          for (uint32_t off = 0; off < w_bytes; off += 32768) {
-            const uint32_t n = min(32768u, w_bytes - off);
-            bulk_g2s(smem_u32(W1 + off), p.w1img + off, n, BAR(14));
-            bulk_g2s(smem_u32(W2 + off), p.w2img + off, n, BAR(14));
-          }
+          mbar_expect_tx(BAR(14), w_bytes + w2_bytes);
+          for (uint32_t off = 0; off < w_bytes; off += 32768)
+            bulk_g2s(smem_u32(W1 + off), p.w1img + off, min(32768u, w_bytes - off), BAR(14));
+          for (uint32_t off = 0; off < w2_bytes; off += 32768)
+            bulk_g2s(smem_u32(W2 + off), p.w2img + off, min(32768u, w2_bytes - off), BAR(14));
         }
       } else if (wid == TC2_ISSUE_WARPS - 1) {
         // ring producer (n_issuers <= 3 in ring mode): one slot per tap, in the issuers' consumption order
@@ -1919,7 +1950,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
         const int K = p.K, ksteps = p.ksteps, m_tiles = p.m_tiles, n_iss = p.n_issuers;
         const uint64_t kb_step16 = (uint64_t)(kblock_bytes >> 4);
         auto run_conv = [&](uint64_t a_tmpl, uint32_t a_hi_addr, uint32_t a_rows, uint32_t a_lo_delta16, uint32_t wsm,
-                            int dil, uint32_t acc) {
+                            int dil, uint32_t acc, int K, int ksteps, uint32_t accum0 = 0u) {   // K taps of `ksteps` k-blocks (shadow the unit's)
           const uint64_t ad0 = a_tmpl + (uint64_t)((a_hi_addr >> 4) & 0x3FFF) + (uint64_t)(wid * 128);
           uint64_t bd = b_tmpl + (uint64_t)((wsm >> 4) & 0x3FFF);
           const uint32_t d0 = acc + (uint32_t)wid * mt_cols;
@@ -1953,11 +1984,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             return;
           }
           if (m_tiles <= n_iss) {   // one M tile per issuer (every plan tc3_plan makes): k-steps unrolled
-            if (ksteps == 1) { issue_conv_1mt<1>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
-            if (ksteps == 2) { issue_conv_1mt<2>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
-            if (ksteps == 4) { issue_conv_1mt<4>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2); return; }
+            if (ksteps == 1) { issue_conv_1mt<1>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2, accum0); return; }
+            if (ksteps == 2) { issue_conv_1mt<2>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2, accum0); return; }
+            if (ksteps == 4) { issue_conv_1mt<4>(ad0, bd, d0, K, (uint64_t)dil, ks_step16, kb_step16, lo_delta, idesc, idesc2, accum0); return; }
           }
-          uint32_t accum = 0u;
+          uint32_t accum = accum0;
           for (int j = 0; j < K; ++j) {
             uint64_t ad = ad0 + (uint64_t)(j * dil);
             for (int ks = 0; ks < ksteps; ++ks, ad += ks_step16, bd += kb_step16) {
@@ -1982,7 +2013,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           }
           tc_fence_after();
           run_conv(a1_tmpl, smem_u32(A1 + (size_t)s * 2 * a1_bytes), (uint32_t)p.x_rows_alloc, a1_bytes >> 4, w1s, p.dil,
-                   tmem_base + (uint32_t)(as * p.acc_cols));
+                   tmem_base + (uint32_t)(as * p.acc_cols), K, ksteps);
           if (!p.pp) umma_commit_elect(BAR(2 + s));   // pp: the buffer stays busy (h in place) until conv2 is done
           umma_commit_elect(BAR(4 + as));
         };
@@ -1991,8 +2022,15 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           if (p.pp) {   // h sits in the tile's own buffer (row stride x_rows), the accumulators are the drained conv1 set
             wa.wait(3, BAR(8 + bs), (uint32_t)((i / 2) & 1), 840 + bs);
             tc_fence_after();
+            if (STK) {   // one tap over 2C channels: h (in place over the x planes), then the raw c planes behind them
+              const uint32_t stage = smem_u32(A1 + (size_t)bs * 2 * a1_bytes);
+              const uint32_t acc = tmem_base + (uint32_t)(bs * p.acc_cols);
+              run_conv(a1_tmpl, stage, (uint32_t)p.x_rows_alloc, a1_bytes >> 4, w2s, 1, acc, 1, ksteps);
+              run_conv(make_kmajor_desc(0, (uint32_t)p.m_out * 16, 128), stage + (uint32_t)(C >> 3) * (uint32_t)p.x_rows_alloc * 16u,
+                       (uint32_t)p.m_out, a1_bytes >> 4, w2s + (uint32_t)ksteps * (uint32_t)kblock_bytes, 1, acc, 1, ksteps, 1u);
+            } else
             run_conv(a1_tmpl, smem_u32(A1 + (size_t)bs * 2 * a1_bytes), (uint32_t)p.x_rows_alloc, a1_bytes >> 4, w2s, 1,
-                     tmem_base + (uint32_t)(bs * p.acc_cols));
+                     tmem_base + (uint32_t)(bs * p.acc_cols), K, ksteps);
             umma_commit_elect(BAR(2 + bs));   // buffer free for the loader
             umma_commit_elect(BAR(10 + bs));
             return;
@@ -2001,7 +2039,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
           if (i >= p.acc2_stages) wa.wait(4, BAR(12 + bs), (uint32_t)((i / p.acc2_stages - 1) & 1), 850 + bs);
           tc_fence_after();
           run_conv(a2_tmpl, smem_u32(A2), (uint32_t)p.h_rows_alloc, a2_bytes >> 4, w2s, 1,
-                   acc2_base + (uint32_t)(bs * p.acc_cols));
+                   acc2_base + (uint32_t)(bs * p.acc_cols), K, ksteps);
           umma_commit_elect(BAR(9));
           umma_commit_elect(BAR(10 + bs));
         };
@@ -2189,7 +2227,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
             float* py = opaque_ptr(yb + (ok ? o0 : 0));
             // split copies: plane kc of half hf at uint4 index (hf * C/8 + kc) * L + t inside the utterance
             const uint32_t q_h0 = (uint32_t)(2 * c) * uL + (uint32_t)(ok ? t : 0), q_lo = (uint32_t)(C >> 3) * uL;
-            if (IO == IO_F32) {
+            if (STK) {   // the skip path is part of conv2's GEMM: nothing to add
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xv[i] = 0.f;
+            } else if (IO == IO_F32) {
               const float* px = opaque_ptr(xb + (ok ? o0 : 0));
 #pragma unroll
               for (int i = 0; i < 16; ++i) xv[i] = ok ? __ldg(px + (uint32_t)i * uL) : 0.f;
@@ -2282,8 +2323,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) conv_tc3_fused_kernel(const Tc
 }
 
 inline size_t tc3_smem_bytes(const Tc3Args& p) {
-  const size_t w = p.w_resident ? 2ULL * p.kblocks * p.C * 64 : (size_t)p.w_stages * p.stage_bytes;
-  return (size_t)p.a1_stages * 2 * p.x_rows_alloc * p.C * 2 + (p.pp ? 0 : 2ULL * p.h_rows_alloc * p.C * 2) + w + 24 * 8;
+  const size_t w = p.w_resident ? (size_t)(p.kblocks + p.kblocks2) * p.C * 64 : (size_t)p.w_stages * p.stage_bytes;
+  return (size_t)p.a1_stages * 2 * (p.x_rows_alloc + (p.stack ? p.m_out : 0)) * p.C * 2 +
+         (p.pp ? 0 : 2ULL * p.h_rows_alloc * p.C * 2) + w + 24 * 8;
 }
 
 // conv1/conv2 must be same-shape C->C convs with K taps (conv2 dilation 1) whose images are single-N-tile (C <= 64).
@@ -2403,6 +2445,7 @@ retry:
   p.tmem_cols = cols;
   p.ksteps = ksteps;
   p.kblocks = kblocks;
+  p.stack = 0; p.k2 = K; p.ksteps2 = ksteps; p.kblocks2 = kblocks; p.reflect = 0; p.ld2_per = p.ld2_rounds = 0;
   p.tiles_per_batch = (L + p.m_out - 1) / p.m_out;
   p.total_tiles = p.tiles_per_batch * B;
   p.idesc = make_idesc_f16(128, C);
@@ -2419,6 +2462,80 @@ retry:
 
 // Is the split (TMA-native) activation path usable at all on this machine?  (driver exports cuTensorMapEncodeTiled)
 inline bool tc3_split_available() { return tma_encode_fn() != nullptr; }
+
+// Launch of a planned fused kernel (ResBlock1 unit or ResidualStack): per-device attributes once, persistent grid, optional PDL,
+// FV_STALL_DEBUG instrumentation.  returns 0 launched, -1 CUDA error.
+inline int tc3_launch(Tc3Args& p, int io, const CUtensorMap& tm_main, const CUtensorMap& tm_tail, cudaStream_t st,
+                      const char* title) {
+  static std::mutex mu;
+  static bool attr_set[64] = {};
+  static int num_sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_set[dev]) {
+      const int mx = 227 * 1024;
+      if (cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+        return -1;
+      cudaDeviceProp prop;
+      if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+      num_sms[dev] = prop.multiProcessorCount;
+      attr_set[dev] = true;
+    }
+  }
+  int gx = std::min(num_sms[dev], p.total_tiles);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(gx, 1, 1);
+  cfg.blockDim = dim3(TC3_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = tc3_smem_bytes(p);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  p.pdl = (tc_pdl_enabled(p.total_tiles, num_sms[dev]) && !tc_stall_debug()) ? 1 : 0;
+  if (p.pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cudaError_t le;
+  if (tc_stall_debug()) {
+    StallReport rep;
+    if (!rep.begin(gx)) return -1;
+    p.dbg = rep.dev;
+    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_F32>, p, tm_main, tm_tail);
+    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
+    else if (io == IO_STACK) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_STACK>, p, tm_main, tm_tail);
+    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_F32>, p, tm_main, tm_tail);
+    static const char* const roles[8] = {"loader", "producer", "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
+    static const char* const slots[8][5] = {{"a1_empty", nullptr, nullptr, nullptr, nullptr},
+                                            {"w_empty", nullptr, nullptr, nullptr, nullptr},
+                                            {"w_full", "a1_full", "acc1_empty", "a2_full", "acc2_empty"},
+                                            {nullptr, nullptr, nullptr, nullptr, nullptr},
+                                            {"acc1_full", "a2_empty", nullptr, nullptr, nullptr},
+                                            {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
+    char full[320];
+    snprintf(full, sizeof full, "%s grid=%d", title, gx);
+    rep.finish(st, full, roles, slots);
+  } else {
+    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_F32>, p, tm_main, tm_tail);
+    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
+    else if (io == IO_STACK) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_STACK>, p, tm_main, tm_tail);
+    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_F32>, p, tm_main, tm_tail);
+  }
+  if (le != cudaSuccess) return -1;
+  g_launches++;
+  g_tc_launches++;
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 // returns 0 launched, 1 not applicable, -1 CUDA error.
 // io = IO_F32: x / y are fp32 [B, C, L].  IO_SPLIT_SPLIT / IO_SPLIT_F32: x is a split-format buffer (fv_tma.cuh) and, for
@@ -2458,6 +2575,242 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
       tm_tail = tm_main;
     }
   }
+  char title[256];
+  snprintf(title, sizeof title,
+           "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d io=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d pp=%d issuers=%d "
+           "tiles=%d", C, K, dil, L, B, acc_mode, io, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
+           p.w_resident, p.w_stages, p.pp, p.n_issuers, p.total_tiles);
+  return tc3_launch(p, io, tm_main, tm_tail, st, title);
+}
+
+// Fused ResidualStack (Tc3Args::stack): y = W_1x1 * lrelu(conv_dil(reflect_pad(lrelu(c))) + b_dil) + W_skip * c + (b_1x1 + b_skip)
+// (modules.py:372-382) in one launch.  l1 = the dilated conv's image, l2 = the pair image [W_1x1 ; W_skip] (Cin = 2C, one tap),
+// b2 = the summed bias.  returns 0 launched, 1 not applicable (the caller runs the two-launch path), -1 CUDA error.
+inline bool tc3_plan_stack(int B, int C, int L, int K, int dil, Tc3Args& p) {
+  if (C % 16 || C > 64 || K % 2 == 0 || K < 3) return false;
+  if ((long long)C * L >= 0x7fffffffLL - 65536) return false;   // 32-bit offsets inside the utterance plane
+  const int ksteps = C / 16, kblocks = K * ksteps, kblocks2 = 2 * ksteps;
+  const long long BUDGET = 225 * 1024;
+  static const int force_m = getenv("FV_STACK_M") ? atoi(getenv("FV_STACK_M")) : 0;   // tuning knob
+  int best_m = 0;
+  double best_sc = -1;
+  for (int m = 8; m >= 1; --m) {
+    if (force_m > 0 && m != force_m) continue;
+    if (2 * m * 2 * C > 512) continue;                           // two accumulator sets (ping-pong tiles)
+    const long long x_rows = 128LL * m + (long long)(K - 1) * dil;
+    const long long sm = 2 * 2 * (x_rows + 128LL * m) * C * 2 + (long long)(kblocks + kblocks2) * C * 64 + 256;
+    if (sm > BUDGET) continue;
+    const long long tiles = (long long)((L + 128 * m - 1) / (128 * m)) * B;
+    const long long gx = std::min<long long>(148, tiles);
+    const long long waves = (tiles + gx - 1) / gx;
+    double sc = (double)tiles / (double)(waves * gx);            // wave balance
+    sc *= (double)(128 * m) / (double)x_rows;                    // halo re-read
+    if (waves < 4) sc *= 0.8;                                    // the two-tile pipeline needs a few tiles per CTA to fill
+    if (sc > best_sc + 1e-9) { best_sc = sc; best_m = m; }
+  }
+  if (best_m == 0) return false;
+  p.B = B; p.C = C; p.L = L; p.K = K; p.dil = dil;
+  p.m_tiles = best_m;
+  p.x_rows = 128 * best_m + (K - 1) * dil;
+  p.x_rows_alloc = p.x_rows;
+  p.h_rows_alloc = p.x_rows;
+  p.m_out = 128 * best_m;
+  p.a1_stages = 2; p.acc1_stages = 2; p.acc2_stages = 2;
+  p.w_resident = 1; p.pp = 1; p.w_stages = 0; p.stage_bytes = 0;
+  p.n_issuers = std::min(best_m, TC2_ISSUE_WARPS);
+  p.acc_cols = best_m * 2 * C;
+  int cols = 32;
+  while (cols < 2 * p.acc_cols) cols <<= 1;
+  p.tmem_cols = cols;
+  p.ksteps = ksteps; p.kblocks = kblocks;
+  p.stack = 1; p.k2 = 1; p.ksteps2 = 2 * ksteps; p.kblocks2 = kblocks2;
+  p.tiles_per_batch = (L + p.m_out - 1) / p.m_out;
+  p.total_tiles = p.tiles_per_batch * B;
+  p.idesc = make_idesc_f16(128, C);
+  p.idesc2 = make_idesc_f16(128, 2 * C);
+  flat_plan((C / 8) * p.x_rows, p.ld_per, p.ld_rounds);
+  flat_plan((C / 8) * p.m_out, p.ld2_per, p.ld2_rounds);
+  return true;
+}
+
+inline int launch_fused_stack(const float* c, float* y, const float* b1, const float* b2, const TcLayer& l1, const TcLayer& l2,
+                              int B, int C, int L, int K, int dil, float slope, bool reflect, cudaStream_t st,
+                              const int* lens = nullptr) {
+  if (!l1.eligible || !l2.eligible || !l1.image || !l2.image || l1.n_tiles != 1 || l2.n_tiles != 1) return 1;
+  if (l1.NT != C || l2.NT != C) return 1;
+  if (!(slope >= 0.f && slope <= 1.f)) return 1;   // lrelu01
+  tc_apply_env_once();
+  Tc3Args p{};
+  if (!tc3_plan_stack(B, C, L, K, dil, p)) return 1;
+  p.x = c; p.y = y; p.bias1 = b1; p.bias2 = b2; p.lens = lens;
+  p.inv_slope = 1.f; p.epi_groups = 1; p.pair_issue = 0;
+  p.w1img = l1.image; p.w2img = l2.image;
+  p.slope = slope; p.acc_mode = ACC_STORE; p.acc_div = 1.f;
+  p.reflect = reflect ? 1 : 0;
+  CUtensorMap tm_main, tm_tail;
+  memset(&tm_main, 0, sizeof tm_main);
+  memset(&tm_tail, 0, sizeof tm_tail);
+  char title[256];
+  snprintf(title, sizeof title, "tc3-stack C=%d K=%d dil=%d L=%d B=%d | mt=%d x_rows=%d issuers=%d tiles=%d", C, K, dil, L, B,
+           p.m_tiles, p.x_rows, p.n_issuers, p.total_tiles);
+  return tc3_launch(p, IO_STACK, tm_main, tm_tail, st, title);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_narrow7_staged_kernel: the HBM-bound k = 7 output convs (conv_post 16 -> 1, LastLayer 32 -> 1, MB conv_post 64 -> 4) with
+// the input streamed through shared memory by the bulk-copy engine.  conv_narrow7_kernel (fv_kernels.cuh) reads every sample
+// three times through L1 with at most six 16-byte loads in flight per thread and reaches 0.53 of the HBM peak; here a persistent
+// CTA keeps N7_STAGES stages of [16 channels][N7_TL + 8 samples] in flight (cp.async.bulk per channel row, mbarrier
+// complete_tx), every sample crosses L1 once, and the threads read their 12-sample windows from shared memory (conflict-free
+// 16-byte reads).  Channels are walked in groups of 16 per stage with the accumulators kept in registers across the groups of a
+// tile, so any Cin % 16 == 0 fits.  Same sums in the same order as conv_narrow7_kernel: identical bits.
+// Algorithmic bytes per position: 4 * (Cin + N).
+// ------------------------------------------------------------------------------------------------
+constexpr int N7_TL = 1024;      // positions per tile = 4 per thread x 256 threads
+constexpr int N7_STAGES = 3;
+constexpr int N7_ROW = N7_TL + 8;
+template <int NOUT>
+__global__ void __launch_bounds__(256, 1) conv_narrow7_staged_kernel(const ConvArgs a, int tiles_per_b, int total_tiles) {
+  constexpr int K = 7, PADL = 3, T = 4;
+  extern __shared__ __align__(128) uint8_t n7_smem[];
+  float* stage0 = reinterpret_cast<float*>(n7_smem);                                   // [N7_STAGES][16][N7_ROW]
+  float* wsm = stage0 + N7_STAGES * 16 * N7_ROW;                                       // [Cin][NOUT][8] (tap 7 = 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + a.Cin * NOUT * 8);
+  const uint32_t bar0 = smem_u32(bars);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.Cin * NOUT * 8; i += blockDim.x) {
+    const int j = i & 7, n = (i >> 3) % NOUT, ci = i / (8 * NOUT);
+    wsm[i] = (j < K && n < a.N) ? __ldg(a.w + ((long long)ci * K + j) * a.N + n) : 0.f;   // derived image is [Cin][K][N]
+  }
+  if (tid == 0) {
+    for (int s = 0; s < N7_STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ngroups = a.Cin >> 4;
+  int n_my = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) ++n_my;
+  const int n_iters = n_my * ngroups;
+  // stage `it`: channels [16*cg, 16*cg + 16) of tile (it / ngroups), samples [t0 - 4, t0 + N7_TL + 4) clipped to the row
+  auto issue = [&](int it) {   // warp 0, converged
+    const int lt = it / ngroups, cg = it - lt * ngroups;
+    const int tile = blockIdx.x + lt * (int)gridDim.x;
+    const int b = tile / tiles_per_b;
+    const int t0 = (tile - b * tiles_per_b) * N7_TL;
+    const int lo = max(t0 - 4, 0), hi = min(t0 + N7_TL + 4, a.Lin);
+    const uint32_t bytes = (uint32_t)(hi - lo) * 4u;
+    const int s = it % N7_STAGES;
+    const uint32_t bar = bar0 + 8u * s;
+    const int lane = tid & 31;
+    if (lane == 0) mbar_expect_tx(bar, 16u * bytes);
+    __syncwarp();
+    if (lane < 16) {
+      const float* src = a.x + (long long)b * a.x_bs + (long long)(cg * 16 + lane) * a.Lin + lo;
+      bulk_g2s(smem_u32(stage0 + ((size_t)s * 16 + lane) * N7_ROW + (lo - (t0 - 4))), src, bytes, bar);
+    }
+  };
+  if (tid < 32)
+    for (int it = 0; it < N7_STAGES && it < n_iters; ++it) issue(it);
+  const float slope = a.pre_slope;
+  float acc[NOUT][T];
+  for (int it = 0; it < n_iters; ++it) {
+    const int lt = it / ngroups, cg = it - lt * ngroups;
+    const int tile = blockIdx.x + lt * (int)gridDim.x;
+    const int b = tile / tiles_per_b;
+    const int tt = (tile - b * tiles_per_b) * N7_TL;
+    const int t0 = tt + T * tid;                         // this thread's first output
+    const int Lb = a.lens ? __ldg(a.lens + b) : a.Lin;
+    const int s = it % N7_STAGES;
+    if (cg == 0) {
+#pragma unroll
+      for (int n = 0; n < NOUT; ++n)
+#pragma unroll
+        for (int q = 0; q < T; ++q) acc[n][q] = 0.f;
+    }
+    mbar_wait(bar0 + 8u * s, (uint32_t)((it / N7_STAGES) & 1), 700 + s);
+    if (t0 < a.Lpos) {
+      if (t0 - 4 >= 0 && t0 + T + 4 <= Lb && t0 + T <= a.Lpos) {   // interior: the whole 12-sample window is real data
+        const float* st = stage0 + (size_t)s * 16 * N7_ROW + T * tid;
+#pragma unroll 4
+        for (int c = 0; c < 16; ++c) {
+          const float4* xr = reinterpret_cast<const float4*>(st + c * N7_ROW);
+          float w[T + 8];
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            const float4 f = xr[v];
+            w[4 * v] = f.x; w[4 * v + 1] = f.y; w[4 * v + 2] = f.z; w[4 * v + 3] = f.w;
+          }
+#pragma unroll
+          for (int i = 1; i < T + 7; ++i) w[i] = pre_act(w[i], slope);   // w[0], w[11] are never used (window t0-3 .. t0+6)
+          const int ci = cg * 16 + c;
+#pragma unroll
+          for (int n = 0; n < NOUT; ++n) {
+            const float4 c0 = *reinterpret_cast<const float4*>(wsm + (ci * NOUT + n) * 8);
+            const float4 c1 = *reinterpret_cast<const float4*>(wsm + (ci * NOUT + n) * 8 + 4);
+            const float cw[7] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+#pragma unroll
+              for (int q = 0; q < T; ++q) acc[n][q] = fmaf(cw[j], w[q + j + (4 - PADL)], acc[n][q]);
+          }
+        }
+      } else {   // padding / ragged end / tail: scalar taps with the generic index rules, straight from global memory
+        const float* xb = a.x + (long long)b * a.x_bs;
+        for (int c = 0; c < 16; ++c) {
+          const int ci = cg * 16 + c;
+          const float* xr = xb + (long long)ci * a.Lin;
+          for (int j = 0; j < K; ++j) {
+#pragma unroll
+            for (int q = 0; q < T; ++q) {
+              int g = t0 + q - PADL + j;
+              if (a.pad_mode == PAD_REFLECT) {
+                if (g < 0) g = -g;
+                if (g >= Lb) g = 2 * (Lb - 1) - g;
+              }
+              const float xv = (g >= 0 && g < Lb) ? pre_act(__ldg(xr + g), slope) : 0.f;
+#pragma unroll
+              for (int n = 0; n < NOUT; ++n) acc[n][q] = fmaf(wsm[(ci * NOUT + n) * 8 + j], xv, acc[n][q]);
+            }
+          }
+        }
+      }
+      if (cg == ngroups - 1) {
+        float* yb = a.y + (long long)b * a.y_bs;
+#pragma unroll
+        for (int n = 0; n < NOUT; ++n) {
+          if (n >= a.N) break;
+          const float bv = a.bias ? __ldg(a.bias + n) : 0.f;
+          float o[T];
+#pragma unroll
+          for (int q = 0; q < T; ++q) {
+            o[q] = acc[n][q] + bv;
+            if (a.post_tanh) o[q] = tanhf(o[q]);
+          }
+          float* yo = yb + (long long)n * a.Lpos + t0;
+          if (t0 + 4 <= a.Lpos) {
+            *reinterpret_cast<float4*>(yo) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int q = 0; q < 4 && t0 + q < a.Lpos; ++q) yo[q] = o[q];
+          }
+        }
+      }
+    }
+    __syncthreads();                                     // every thread is done with stage s
+    if (tid < 32 && it + N7_STAGES < n_iters) issue(it + N7_STAGES);
+  }
+}
+inline size_t n7_staged_smem(const ConvArgs& a, int nout) {
+  return (size_t)N7_STAGES * 16 * N7_ROW * sizeof(float) + (size_t)a.Cin * nout * 8 * sizeof(float) + N7_STAGES * 8 + 128;
+}
+inline bool conv_narrow7_staged_ok(const ConvArgs& a) {
+  // Measured (gpurun r2v, B = 32, T = 1000): conv_post 16 -> 1 0.150 -> 0.20 ms (SLOWER: one 256-thread CTA per SM cannot hide
+  // the shared-memory / FMA latency the 32-warp occupancy of conv_narrow7_kernel hides), LastLayer 32 -> 1 0.400 -> 0.385 ms,
+  // MB conv_post 64 -> 4 0.81 ms against 0.48 ms on tcgen05 -> opt-in only (FV_NARROW7_STAGED=1); bit-identical either way (test).
+  static const bool env = getenv("FV_NARROW7_STAGED") != nullptr && atoi(getenv("FV_NARROW7_STAGED")) != 0;
+  return env && conv_narrow7_ok(a) && a.Cin % 16 == 0 && a.Lin >= N7_TL && n7_staged_smem(a, a.N == 1 ? 1 : (a.N == 2 ? 2 : 4)) <= 225 * 1024;
+}
+// returns cudaSuccess when launched
+inline cudaError_t launch_conv_narrow7_staged(const ConvArgs& a, cudaStream_t st) {
   static std::mutex mu;
   static bool attr_set[64] = {};
   static int num_sms[64] = {};
@@ -2468,63 +2821,27 @@ inline int launch_fused_unit(const float* x, float* y, const float* b1, const fl
     std::lock_guard<std::mutex> lk(mu);
     if (!attr_set[dev]) {
       const int mx = 227 * 1024;
-      if (cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc3_fused_kernel<false, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
-          cudaFuncSetAttribute(conv_tc3_fused_kernel<true, IO_SPLIT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
-        return -1;
+      cudaError_t e;
+      if ((e = cudaFuncSetAttribute(conv_narrow7_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(conv_narrow7_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
+      if ((e = cudaFuncSetAttribute(conv_narrow7_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx)) != cudaSuccess) return e;
       cudaDeviceProp prop;
-      if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1;
+      if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return e;
       num_sms[dev] = prop.multiProcessorCount;
       attr_set[dev] = true;
     }
   }
-  int gx = std::min(num_sms[dev], p.total_tiles);
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(gx, 1, 1);
-  cfg.blockDim = dim3(TC3_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = tc3_smem_bytes(p);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  p.pdl = (tc_pdl_enabled(p.total_tiles, num_sms[dev]) && !tc_stall_debug()) ? 1 : 0;
-  if (p.pdl) {
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  }
-  cudaError_t le;
-  if (tc_stall_debug()) {
-    StallReport rep;
-    if (!rep.begin(gx)) return -1;
-    p.dbg = rep.dev;
-    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_F32>, p, tm_main, tm_tail);
-    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
-    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<true, IO_SPLIT_F32>, p, tm_main, tm_tail);
-    static const char* const roles[8] = {"loader", "producer", "issuer0", nullptr, "epiA", "epiB", nullptr, nullptr};
-    static const char* const slots[8][5] = {{"a1_empty", nullptr, nullptr, nullptr, nullptr},
-                                            {"w_empty", nullptr, nullptr, nullptr, nullptr},
-                                            {"w_full", "a1_full", "acc1_empty", "a2_full", "acc2_empty"},
-                                            {nullptr, nullptr, nullptr, nullptr, nullptr},
-                                            {"acc1_full", "a2_empty", nullptr, nullptr, nullptr},
-                                            {"acc2_full", nullptr, nullptr, nullptr, nullptr}};
-    char title[256];
-    snprintf(title, sizeof title,
-             "tc3 C=%d K=%d dil=%d L=%d B=%d acc=%d io=%d | mt=%d m_out=%d a1_st=%d acc1_st=%d acc2_st=%d resident=%d w_st=%d pp=%d issuers=%d "
-             "tiles=%d grid=%d", C, K, dil, L, B, acc_mode, io, p.m_tiles, p.m_out, p.a1_stages, p.acc1_stages, p.acc2_stages,
-             p.w_resident, p.w_stages, p.pp, p.n_issuers, p.total_tiles, gx);
-    rep.finish(st, title, roles, slots);
-  } else {
-    if (io == IO_F32) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_F32>, p, tm_main, tm_tail);
-    else if (io == IO_SPLIT_SPLIT) le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_SPLIT>, p, tm_main, tm_tail);
-    else le = cudaLaunchKernelEx(&cfg, conv_tc3_fused_kernel<false, IO_SPLIT_F32>, p, tm_main, tm_tail);
-  }
-  if (le != cudaSuccess) return -1;
+  const int tiles_per_b = (a.Lpos + N7_TL - 1) / N7_TL;
+  const long long total = (long long)tiles_per_b * a.B;
+  if (total >= 0x7fffffffLL) return cudaErrorInvalidValue;
+  const int grid = (int)std::min<long long>(num_sms[dev], total);
+  const int nout = a.N == 1 ? 1 : (a.N == 2 ? 2 : 4);
+  const size_t smem = n7_staged_smem(a, nout);
+  if (nout == 1) conv_narrow7_staged_kernel<1><<<grid, 256, smem, st>>>(a, tiles_per_b, (int)total);
+  else if (nout == 2) conv_narrow7_staged_kernel<2><<<grid, 256, smem, st>>>(a, tiles_per_b, (int)total);
+  else conv_narrow7_staged_kernel<4><<<grid, 256, smem, st>>>(a, tiles_per_b, (int)total);
   g_launches++;
-  g_tc_launches++;
-  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+  return cudaGetLastError();
 }
 
 }  // namespace fv

@@ -323,7 +323,7 @@ class _NativeGenerator(torch.nn.Module):
             _lib.check(_lib.lib().fv_forward_profile(self._handle, _lib.ptr(x), B, T, _lib.ptr(out), None,
                                                      _lib.ptr(ws), ws.numel(), flags, _lib.current_stream_ptr(),
                                                      entries, cap, C.byref(n)), "fv_forward_profile")
-        kn = {0: "ffma", 1: "tcgen05", 2: "tcgen05-fused-unit"}
+        kn = {0: "ffma", 1: "tcgen05", 2: "tcgen05-fused-unit", 3: "tcgen05-fused-stack"}
         return [dict(name=e.name.decode(), kernel=kn.get(e.kernel, str(e.kernel)), Cin=e.Cin, N=e.N, K=e.K,
                      dil=e.dil, positions=e.positions, flops=e.flops, bytes=e.bytes, ms=e.ms)
                 for e in entries[: n.value]]

@@ -174,7 +174,8 @@ int fv_forward_flops(const fv_handle* h, int B, int T, int flags, double* flops)
  * All pointers are device pointers.  `pad_mode`: 0 zero, 1 reflect.  `pre_slope` < 0 disables the
  * LeakyReLU applied to the input before the convolution (0 = ReLU).  `residual` may be NULL.
  * `use_tc` != 0 routes through the tcgen05 path when the shape is eligible (fv_resblock1: 2 = fused-unit kernel,
- * 3 = fused units chained through the TMA-fed split fp16 hi/lo activation format).
+ * 3 = fused units chained through the TMA-fed split fp16 hi/lo activation format; fv_residual_stack: 2 = the fused
+ * ResidualStack kernel when the shape is eligible, else layer by layer, 3 = the fused kernel or FV_EINVAL).
  *
  * fv_conv1d            <- torch.nn.Conv1d call sites (modules.py:193-220,364,366,377; hifigan.py:93,105)
  * fv_conv_transpose1d  <- torch.nn.ConvTranspose1d call sites (hifigan.py:39-44, melgan.py:77-85)

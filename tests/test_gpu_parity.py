@@ -724,3 +724,111 @@ def test_host_pipeline_matches_direct_forward(specs):
         pipe.finish()
         for w, o in zip(want, outs):
             assert torch.equal(w, o)
+
+
+def _residual_stack_ref(x, p, d):
+    """ResidualStack.forward (modules.py:372-382) in fp64 torch: stack(c) + skip_layer(c)."""
+    F = torch.nn.functional
+    c = torch.from_numpy(x).double()
+    t = {k: torch.from_numpy(v).double() for k, v in p.items()}
+    h = F.conv1d(F.pad(F.leaky_relu(c, 0.2), (d, d), mode="reflect"), t["w_dil"], t["b_dil"], dilation=d)
+    return (F.conv1d(F.leaky_relu(h, 0.2), t["w_1x1"], t["b_1x1"]) + F.conv1d(c, t["w_skip"], t["b_skip"])).numpy()
+
+
+@pytest.mark.parametrize("C,d,L,B", [(32, 1, 700, 2), (32, 3, 1000, 3), (32, 9, 50, 2), (32, 9, 2500, 1), (64, 1, 300, 3),
+                                     (64, 3, 129, 2), (64, 9, 1111, 2), (16, 9, 4000, 2), (48, 3, 515, 1)])
+def test_fused_residual_stack_kernel(C, d, L, B):
+    """Dilated conv (reflect pad) -> LeakyReLU -> [1x1 | skip 1x1] pair fused in one tcgen05 kernel (h stays in shared
+    memory, c read once) vs the fp64 restatement of ResidualStack.forward, and vs the layer-by-layer tcgen05 path."""
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    rng = np.random.default_rng(C * 10 + d)
+    x = rng.standard_normal((B, C, L)).astype(np.float32)
+    p = {"w_dil": (rng.standard_normal((C, C, 3)) * (0.6 / np.sqrt(3 * C))).astype(np.float32),
+         "b_dil": (rng.standard_normal(C) * 0.1).astype(np.float32),
+         "w_1x1": (rng.standard_normal((C, C, 1)) * (0.6 / np.sqrt(C))).astype(np.float32),
+         "b_1x1": (rng.standard_normal(C) * 0.1).astype(np.float32),
+         "w_skip": (rng.standard_normal((C, C, 1)) * (0.6 / np.sqrt(C))).astype(np.float32),
+         "b_skip": (rng.standard_normal(C) * 0.1).astype(np.float32)}
+    want = _residual_stack_ref(x, p, d)
+    t = {k: dev(v) for k, v in p.items()}
+    dx = dev(x)
+    scratch = torch.empty(2 * B * C * L, device="cuda")
+    outs = {}
+    for mode in (3, 1):
+        y = torch.full((B, C, L), float("nan"), device="cuda")
+        n0 = _lib.lib().fv_launch_count()
+        _lib.check(_lib.lib().fv_residual_stack(_lib.ptr(dx), _lib.ptr(t["w_dil"]), _lib.ptr(t["b_dil"]), _lib.ptr(t["w_1x1"]),
+                                                _lib.ptr(t["b_1x1"]), _lib.ptr(t["w_skip"]), _lib.ptr(t["b_skip"]), _lib.ptr(y),
+                                                _lib.ptr(scratch), B, C, L, 3, d, mode, stream()))
+        outs[mode] = y.cpu().numpy()
+        assert not np.isnan(outs[mode]).any()
+    err = np.abs(outs[3] - want).max()
+    assert err < 2e-5, err
+    assert np.abs(outs[3] - outs[1]).max() < 2e-5
+
+
+@pytest.mark.parametrize("key", ["melgan-original", "melgan-nobias-slope01"])
+def test_fused_stack_model_matches_reference(specs, key):
+    """MelGAN forward with the fused ResidualStack kernel (default) vs the reference golden; the fused kernel is really used."""
+    if TC_DISABLED:
+        pytest.skip("FV_DISABLE_TC set")
+    g = load_model_golden(key)
+    m = make_model(specs, key)
+    x = dev(g["mel"])
+    with torch.no_grad():
+        y = m(x)
+    prof = m.profile_forward(x)
+    kinds = [r["kernel"] for r in prof]
+    assert kinds.count("tcgen05-fused-stack") == 6, kinds        # the C = 64 and C = 32 stages: 3 stacks each
+    assert np.abs(y.cpu().numpy() - g["forward0_f32"]).max() < TOL
+    assert np.abs(y.cpu().numpy() - g["forward0_f64"]).max() < TIGHT
+
+
+_STREAM_KERNEL_SCRIPT = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from fastvocoder_b200 import PQMF, _lib
+rng = np.random.default_rng(5)
+out = {}
+pq = PQMF().cuda()
+xs = torch.from_numpy(rng.standard_normal((3, 4, 5000)).astype(np.float32)).cuda()
+out["syn"] = pq.synthesis(xs).cpu().numpy()
+xa = torch.from_numpy(rng.standard_normal((3, 1, 20000)).astype(np.float32)).cuda()
+out["ana"] = pq.analysis(xa).cpu().numpy()
+for name, (Cin, Cout, L, pad_mode, slope, tanh) in {"post": (16, 1, 5000, 0, 0.01, 1), "last": (32, 1, 3076, 1, 0.2, 1),
+                                                   "mb": (64, 4, 2048, 0, 0.01, 1), "short": (16, 1, 1024, 0, 0.01, 1)}.items():
+    x = torch.from_numpy(rng.standard_normal((2, Cin, L)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((Cout, Cin, 7)) / np.sqrt(7 * Cin)).astype(np.float32)).cuda()
+    b = torch.from_numpy((rng.standard_normal(Cout) * 0.1).astype(np.float32)).cuda()
+    y = torch.full((2, Cout, L), float("nan"), device="cuda")
+    _lib.check(_lib.lib().fv_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), None, _lib.ptr(y), 2, Cin, Cout, L, 7, 1, pad_mode,
+                                    slope, tanh, 0, _lib.current_stream_ptr()))
+    out[name] = y.cpu().numpy()
+    out[name + "_x"], out[name + "_w"], out[name + "_b"] = x.cpu().numpy(), w.cpu().numpy(), b.cpu().numpy()
+np.savez(sys.argv[2], **out)
+'''
+
+
+def test_streaming_kernel_variants_are_bit_identical(tmp_path):
+    """The vectorised PQMF kernels and the bulk-copy staged k = 7 output conv add the same products in the same order as the
+    kernels they replace (FV_PQMF_V4=0 / FV_NARROW7_STAGED=0): identical bits, and both agree with the fp64 oracle."""
+    import subprocess
+    import sys
+    script = tmp_path / "variants.py"
+    script.write_text(_STREAM_KERNEL_SCRIPT)
+    res = {}
+    for tag, env in (("new", {"FV_NARROW7_STAGED": "1"}), ("old", {"FV_PQMF_V4": "0", "FV_NARROW7_STAGED": "0"})):
+        f = tmp_path / f"{tag}.npz"
+        r = subprocess.run([sys.executable, str(script), REPO, str(f)], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr[-3000:]
+        res[tag] = dict(np.load(f))
+    for k in ("syn", "ana", "post", "last", "mb", "short"):
+        assert not np.isnan(res["new"][k]).any()
+        assert np.array_equal(res["new"][k], res["old"][k]), k
+    F = torch.nn.functional
+    for k, (pad_mode, slope) in {"post": ("constant", 0.01), "last": ("reflect", 0.2), "mb": ("constant", 0.01)}.items():
+        x, w, b = (torch.from_numpy(res["new"][k + s]).double() for s in ("_x", "_w", "_b"))
+        want = torch.tanh(F.conv1d(F.pad(F.leaky_relu(x, slope), (3, 3), mode=pad_mode), w, b)).numpy()
+        assert np.abs(res["new"][k] - want).max() < 2e-6, k
