@@ -71,6 +71,7 @@ _F = C.c_float
 SIGNATURES = {
     "fv_last_error": (C.c_char_p, []),
     "fv_abi_version": (_I, []),
+    "fv_tc_usable": (C.c_int, [C.c_void_p]),
     "fv_launch_count": (C.c_int64, []),
     "fv_tc_launch_count": (C.c_int64, []),
     "fv_create": (_I, [C.POINTER(FvConfig), C.POINTER(_P)]),

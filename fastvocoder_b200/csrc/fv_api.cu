@@ -324,7 +324,7 @@ static int forward_impl(fv_handle* h, const float* mel, int B, int T, float* out
   const fv_config& c = m.cfg;
   static const bool tc_disabled_env = getenv("FV_DISABLE_TC") != nullptr;
   static const bool fuse_disabled_env = getenv("FV_NO_FUSE") != nullptr;
-  const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES) && !tc_disabled_env;
+  const bool tc_ok = !(flags & FV_FWD_NO_TENSOR_CORES) && !tc_disabled_env && h->tc.buf != nullptr;   // (images dropped: fv_tc_usable)
   const bool fuse_ok = !fuse_disabled_env;
   // MRF sum on the tensor-core path: 1/num_kernels folded into every branch and accumulated with red.global.add (no read of
   // the running sum in the epilogues); the exact-fp32 path keeps the reference's add-then-divide order.  FV_MRF_RED=0: off.
@@ -848,9 +848,18 @@ int fv_bind_weights(fv_handle* h, const float* packed_dev, int64_t n_floats, con
   h->pqmf_ana = pqmf_analysis_dev;
   h->pqmf_syn = pqmf_synthesis_dev;
   FV_CUDA(cudaStreamSynchronize(st));
+  if (!h->tc.in_range()) {
+    // |w| > 65504 (or a non-finite weight): cvt.satfinite would clamp it silently in the fp16 hi/lo images.  Drop them: every
+    // layer of this handle then runs on the exact-fp32 kernels (still on the GPU), and fv_tc_usable() reports it.
+    h->tc.release();
+    fprintf(stderr, "fastvocoder_b200: a weight exceeds the fp16 split range (|w| > 65504 or non-finite); "
+                    "this handle runs on the exact-fp32 kernels\n");
+  }
   h->bound = true;
   return FV_OK;
 }
+
+int fv_tc_usable(const fv_handle* h) { return (h && h->bound && h->tc.buf) ? 1 : 0; }
 
 int fv_out_length(const fv_handle* h, int T, int flags, int64_t* out_len) {
   if (!h || !out_len || T <= 0) return fail(FV_EINVAL, "bad argument");

@@ -404,7 +404,7 @@ inline void flat_plan(int nitems, int& per, int& rounds) {
 // Weight image (bind time): fp32 derived image [Cin][Kd][N] -> fp16 hi/lo UMMA-canonical blocks
 // ------------------------------------------------------------------------------------------------
 __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __restrict__ img, int Cin, int Kd, int N,
-                                       int Npad, int NT) {
+                                       int Npad, int NT, int* __restrict__ range_flag) {
   const int ksteps = Cin / 16;
   const long long total = (long long)Cin * Kd * Npad;  // one thread per (padded) weight
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -413,7 +413,9 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ wd, uint8_t* __
     const int j = (int)(q % Kd);
     const int ci = (int)(q / Kd);
     __half hi, lo;
-    split_f16(n < N ? wd[q * N + n] : 0.f, hi, lo);
+    const float wv = n < N ? wd[q * N + n] : 0.f;
+    if (!(fabsf(wv) <= 65504.f) && range_flag) *range_flag = 1;   // outside the fp16 hi/lo range (or NaN): the split would clamp it
+    split_f16(wv, hi, lo);
     const int nt = n / NT, nn = n - nt * NT;
     const int ks = ci >> 4, kc2 = (ci >> 3) & 1, e = ci & 7;
     const long long kb = (long long)j * ksteps + ks;
@@ -437,6 +439,7 @@ inline int tc_pick_nt(int N) {
 struct TcWeights {
   std::vector<TcLayer> layers;
   uint8_t* buf = nullptr;
+  int* range_flag = nullptr;   // device int behind the images: set by the pack kernel when a weight does not fit the fp16 split
 
   int build(const std::vector<Layer>& ls, const float* derived, cudaStream_t st) {
     release();
@@ -459,7 +462,9 @@ struct TcWeights {
       total += ((int64_t)l.Cin * l.Kd * npad * 4 + 255) / 256 * 256;
     }
     if (total == 0) return 0;
-    if (cudaMalloc(&buf, (size_t)total) != cudaSuccess) return -1;
+    if (cudaMalloc(&buf, (size_t)total + 256) != cudaSuccess) return -1;
+    range_flag = reinterpret_cast<int*>(buf + total);
+    if (cudaMemsetAsync(range_flag, 0, sizeof(int), st) != cudaSuccess) return -1;
     for (size_t i = 0; i < ls.size(); ++i) {
       if (!layers[i].eligible) continue;
       layers[i].image = buf + layers[i].img_offset;
@@ -468,15 +473,22 @@ struct TcWeights {
       long long g = (n + 255) / 256;
       if (g > 148 * 16) g = 148 * 16;
       tc_pack_weights_kernel<<<(int)g, 256, 0, st>>>(derived + l.wd_offset, buf + layers[i].img_offset, l.Cin, l.Kd,
-                                                     l.N, layers[i].n_pad, layers[i].NT);
+                                                     l.N, layers[i].n_pad, layers[i].NT, range_flag);
       g_launches++;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
   }
   const TcLayer* layer(int i) const { return (buf && i < (int)layers.size()) ? &layers[i] : nullptr; }
+  // after the stream has been synchronised: did every weight fit the split?  (false -> the caller drops the images: exact fp32 path)
+  bool in_range() const {
+    int f = 0;
+    if (range_flag && cudaMemcpy(&f, range_flag, sizeof f, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    return f == 0;
+  }
   void release() {
     if (buf) cudaFree(buf);
     buf = nullptr;
+    range_flag = nullptr;
     layers.clear();
   }
 };

@@ -230,6 +230,13 @@ class _NativeGenerator(torch.nn.Module):
                                                       _lib.current_stream_ptr()), "fv_bind_weights")
             self._bound_key = key
 
+    @property
+    def tensor_cores_usable(self) -> bool:
+        """False when a bound weight does not fit the fp16 hi/lo split (|w| > 65504 or non-finite): the library then dropped the
+        tensor-core images and every layer runs on the exact-fp32 kernels (fv_tc_usable, include/fastvocoder_b200.h)."""
+        self._ensure_bound()
+        return bool(_lib.lib().fv_tc_usable(self._handle))
+
     def _get_workspace(self, B, T):
         """One workspace per CUDA stream: two streams driving the same model never share activation buffers."""
         need = C.c_size_t()

@@ -129,6 +129,10 @@ int fv_param_info(const fv_handle* h, int index, char* name, int name_cap, int64
 int64_t fv_param_total_floats(const fv_handle* h);
 int fv_bind_weights(fv_handle* h, const float* packed_dev, int64_t n_floats, const float* pqmf_analysis_dev,
                     const float* pqmf_synthesis_dev, void* stream);
+/* 1 when the bound handle holds tensor-core (fp16 hi/lo split) weight images.  fv_bind_weights drops them, and every layer
+ * then runs on the exact-fp32 kernels, when a weight does not fit the split (|w| > 65504 or non-finite: cvt.satfinite would
+ * clamp it silently).  Activations are assumed to stay below 65504 in magnitude on the tensor-core path. */
+int fv_tc_usable(const fv_handle* h);
 
 /* ---- forward -------------------------------------------------------------------------------------
  * fv_out_length  : samples per utterance of `out` for T mel frames (prod(rates)*T; MB: per-band length;

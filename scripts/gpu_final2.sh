@@ -41,6 +41,9 @@ cap pqmf_syn pqmf_synthesis 0 --batch 8        # hbm_kernels leg of the bench: B
 cap encode16 encode16 0 --batch 8
 cap absmax absmax 0 --batch 8
 cap tc2_basis_k3 conv_tc2 6 --model basis-melgan --batch 8
+cap pqmf_ana pqmf_analysis 0 --batch 8         # hbm_kernels leg: 64 x 240000 -> 4 x 60000
+cap stack_c32 conv_tc3 3 --model melgan --batch 8   # fused ResidualStack C=32 (the 4th fused launch of a MelGAN forward)
+cap stack_c64 conv_tc3 0 --model melgan --batch 8   # fused ResidualStack C=64
 cat $OUT/pytest_$TAG.log; tail -2 $OUT/smoke_$TAG.log
 python - <<PY
 import json

@@ -26,7 +26,7 @@ for line in out.splitlines():
     if cur is not None:
         cur.append(line)
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip()
-WANT = ("conv_tc3_fused_kernel", "conv_tc2_kernel", "conv_narrow7", "pqmf_synthesis_poly", "pack_split", "encode16")
+WANT = ("conv_tc3_fused_kernel", "conv_tc2_kernel", "conv_narrow7", "pqmf_synthesis_poly", "pqmf_analysis_v4", "pack_split", "encode16")
 index = []
 for mangled, lines in kernels.items():
     dn = demangle(mangled)

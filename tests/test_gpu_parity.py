@@ -832,3 +832,25 @@ def test_streaming_kernel_variants_are_bit_identical(tmp_path):
         x, w, b = (torch.from_numpy(res["new"][k + s]).double() for s in ("_x", "_w", "_b"))
         want = torch.tanh(F.conv1d(F.pad(F.leaky_relu(x, slope), (3, 3), mode=pad_mode), w, b)).numpy()
         assert np.abs(res["new"][k] - want).max() < 2e-6, k
+
+
+def test_out_of_range_weight_drops_the_tensor_core_images(specs):
+    """A weight the fp16 hi/lo split cannot hold (|w| > 65504) must not be clamped silently: the handle falls back to the exact
+    fp32 kernels (still on the GPU) and says so."""
+    m = make_model(specs, "hifigan-light")
+    assert m.tensor_cores_usable or TC_DISABLED
+    x = dev(synth_mel(1, 24, seed=3))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    k0 = next(k for k in sd if k.endswith("resblocks.0.convs1.0.weight"))
+    sd[k0].view(-1)[0] = 1.0e5
+    m2 = make_model(specs, "hifigan-light")
+    m2.load_state_dict(sd)
+    m2.to("cuda")
+    assert not m2.tensor_cores_usable
+    t0 = _lib.lib().fv_tc_launch_count()
+    with torch.no_grad():
+        y = m2(x)
+    assert _lib.lib().fv_tc_launch_count() == t0
+    m2.use_tensor_cores = False
+    with torch.no_grad():
+        assert torch.equal(y, m2(x))
