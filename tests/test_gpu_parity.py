@@ -629,7 +629,8 @@ def test_batch_equals_single_at_full_length(specs, key):
             assert torch.equal(yb[b:b + 1], ys), (key, b, float((yb[b:b + 1] - ys).abs().max()))
 
 
-KNOBS = [{"FV_SPLIT": "0"}, {"FV_SPLIT_WIDE": "0"}, {"FV_SPLIT_FINAL": "0"}, {"FV_STACK_SPLIT": "0"}, {"FV_TC3_EPI": "1", "FV_TC2_EPI": "1"},
+KNOBS = [{"FV_SPLIT": "0"}, {"FV_SPLIT_WIDE": "0"}, {"FV_SPLIT_FINAL": "0"}, {"FV_STACK_SPLIT": "0"}, {"FV_STACK_FUSED": "0"},
+         {"FV_TC3_EPI": "1", "FV_TC2_EPI": "1"},
          {"FV_TC3_PP": "0"}, {"FV_TC3_PP": "3"}, {"FV_TC3_RING": "0"}, {"FV_MRF_RED": "0"}, {"FV_TC3_ISSUERS": "1"}, {"FV_PDL": "1"},
          {"FV_PDL": "0"}, {"FV_NO_FUSE": "1"}]
 
