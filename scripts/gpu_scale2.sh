@@ -5,7 +5,7 @@
 TAG=${1:-sc2}
 OUT=gpurun_out
 mkdir -p $OUT
-for N in 8 4 2; do
+for N in ${NS:-8 4 2}; do
   timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29540+N)) bench.py --gpus $N --steps 10 --warmup 3 --skip-cpu-baseline > $OUT/scale_n${N}_$TAG.json 2> $OUT/scale_n${N}_$TAG.err
   python - <<PY
 import json
