@@ -69,6 +69,23 @@ static int check_tc3(int B, int C, int L, int K, int dil) {
   return 1;
 }
 
+// fused ResidualStack plans (tc3_plan_stack): ping-pong tiles, resident images of different sizes, raw planes behind the x planes
+static int check_stack(int B, int C, int L, int K, int dil) {
+  Tc3Args p{};
+  if (!tc3_plan_stack(B, C, L, K, dil, p)) return 0;
+  const size_t smem = tc3_smem_bytes(p);
+  CHECK(smem <= 227 * 1024, "stack C=%d K=%d dil=%d smem=%zu", C, K, dil, smem);
+  CHECK(pow2(p.tmem_cols) && p.tmem_cols >= 32 && p.tmem_cols <= 512, "stack C=%d tmem_cols=%d", C, p.tmem_cols);
+  CHECK(2 * p.acc_cols <= p.tmem_cols && p.acc_cols == p.m_tiles * 2 * C, "stack acc %d cols, tmem %d", p.acc_cols, p.tmem_cols);
+  CHECK(p.stack == 1 && p.pp == 1 && p.w_resident == 1 && p.a1_stages == 2 && p.acc1_stages == 2 && p.acc2_stages == 2, "stack mode");
+  CHECK(p.k2 == 1 && p.ksteps2 == 2 * p.ksteps && p.kblocks2 == 2 * p.ksteps && p.kblocks == K * p.ksteps, "stack images");
+  CHECK(p.m_out == 128 * p.m_tiles && p.x_rows == p.m_out + (K - 1) * dil && p.x_rows_alloc >= p.x_rows, "stack rows");
+  CHECK(p.n_issuers >= 1 && p.n_issuers <= TC2_ISSUE_WARPS && p.m_tiles <= p.n_issuers * 4, "stack issuers=%d", p.n_issuers);
+  CHECK(p.ld_per >= 1 && p.ld_per <= LD_MAX && p.ld_rounds >= 1 && 256 * p.ld_per * p.ld_rounds >= (C / 8) * p.x_rows, "stack loader plan");
+  CHECK((long long)p.tiles_per_batch * p.m_out >= L && p.total_tiles == p.tiles_per_batch * B, "stack coverage");
+  return 1;
+}
+
 int main() {
   int planned = 0;
   // every conv-like shape of the shipped configs (channels, taps, dilations), plus odd lengths and batch sizes
@@ -83,6 +100,7 @@ int main() {
               for (int acc : {ACC_STORE, ACC_ADD, ACC_ADD_DIV, ACC_STORE_SCALE, ACC_RED_SCALE})
                 planned += check_tc2(B, C, C, K, d, L, res != 0, acc, OUT_BCL);
             if (C <= 64 && K > 1) planned += check_tc3(B, C, L, K, d);
+            if (C <= 64 && K == 3) planned += check_stack(B, C, L, K, d);
           }
       planned += check_tc2(B, 80, 256, 7, 1, L, false, ACC_STORE, OUT_BCL);      // conv_pre
       planned += check_tc2(B, 80, 512, 7, 1, L, false, ACC_STORE, OUT_BCL);

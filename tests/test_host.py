@@ -162,7 +162,8 @@ def test_tile_planners_respect_hardware_limits(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     env = {k: v for k, v in os.environ.items() if not k.startswith("FV_")}
     variants = [{}, {"FV_TC3_PP": "0"}, {"FV_TC3_PP": "1"}, {"FV_TC3_PP": "3"}, {"FV_TC3_RING": "0"},
-                {"FV_LOADER_FLAT": "2"}, {"FV_A_REUSE": "1"}, {"FV_TC3_RING_M": "1"}]     # every planner knob
+                {"FV_LOADER_FLAT": "2"}, {"FV_A_REUSE": "1"}, {"FV_TC3_RING_M": "1"}, {"FV_STACK_M": "1"},
+                {"FV_STACK_M": "2"}]                                                      # every planner knob
     for extra in variants:
         r = subprocess.run([exe], capture_output=True, text=True, env=dict(env, **extra))
         assert r.returncode == 0, (extra, r.stdout[-3000:])
