@@ -1666,15 +1666,15 @@ struct Tc3Args {
   // with half the TMEM / no separate A2 buffer; the issuers walk pairs: conv1(a) conv1(b) conv2(a) conv2(b).
   int pp;
   // Fused ResidualStack (template parameter IO = IO_STACK, MelGAN family, modules.py:353-382): conv1 = the dilated k-tap conv on
-  // lrelu(c) with reflect padding, conv2 = ONE tap over 2C channels [h | c] with the concatenated image [W_1x1 ; W_skip]
-  // (the stack's 1x1 conv and its skip conv as one GEMM), no residual in epiB.  The loaders put a second, un-activated copy of
-  // the tile's central rows behind the activated planes of the same stage (chunks C/8 .. 2C/8-1, row r = position t0 + r), so
-  // conv2 walks one 2C-channel operand: chunks [0, C/8) = h written in place by epiA, the rest = raw c.  Always ping-pong tiles
-  // with resident weights; h never leaves the SM and c is read once.
+  // lrelu(c) with reflect padding, conv2 = ONE tap over 2C channels [h | c] against the concatenated image [W_1x1 ; W_skip]
+  // (the stack's 1x1 conv and its skip conv as one GEMM), no residual in epiB.  Stage layout per half (hi / lo):
+  // [C/8 activated planes x x_rows_alloc rows (halo included)] [C/8 raw planes x m_out rows (row r = position t0 + r)] — both
+  // written by the loaders from the same loaded registers; epiA writes h in place over the activated planes and conv2 is issued
+  // as two descriptor walks (h planes, then the raw planes, accumulating) over the two halves of its image.  Always ping-pong
+  // tiles with resident weights; h never leaves the SM and c is read once.
   int stack;
   int k2, ksteps2, kblocks2;   // conv2: taps, k-steps per tap, k-blocks of its image (HiFi units: K, ksteps, kblocks)
   int reflect;                 // loaders: ReflectionPad1d instead of zero padding (per utterance length)
-  int ld2_per, ld2_rounds;     // flattened loader plan of the raw copy
   long long* dbg;      // stall-accounting buffer (FV_STALL_DEBUG) or nullptr
 };
 
@@ -2457,7 +2457,7 @@ retry:
   p.tmem_cols = cols;
   p.ksteps = ksteps;
   p.kblocks = kblocks;
-  p.stack = 0; p.k2 = K; p.ksteps2 = ksteps; p.kblocks2 = kblocks; p.reflect = 0; p.ld2_per = p.ld2_rounds = 0;
+  p.stack = 0; p.k2 = K; p.ksteps2 = ksteps; p.kblocks2 = kblocks; p.reflect = 0;
   p.tiles_per_batch = (L + p.m_out - 1) / p.m_out;
   p.total_tiles = p.tiles_per_batch * B;
   p.idesc = make_idesc_f16(128, C);
@@ -2641,7 +2641,6 @@ inline bool tc3_plan_stack(int B, int C, int L, int K, int dil, Tc3Args& p) {
   p.idesc = make_idesc_f16(128, C);
   p.idesc2 = make_idesc_f16(128, 2 * C);
   flat_plan((C / 8) * p.x_rows, p.ld_per, p.ld_rounds);
-  flat_plan((C / 8) * p.m_out, p.ld2_per, p.ld2_rounds);
   return true;
 }
 
