@@ -100,6 +100,13 @@ def test_error_conventions(specs):
     m = build_generator("hifigan", specs["hifigan-light"]["config"])
     with pytest.raises(_lib.FvError, match="no CPU"):
         m(torch.zeros(1, 80, 8))                      # no CPU fallback: must fail loudly
+    with pytest.raises(_lib.FvError, match="no CPU"):
+        m.tensor_cores_usable                         # needs bound (device-resident) weights
+    from fastvocoder_b200 import HostPipeline
+    with pytest.raises(_lib.FvError, match="CUDA"):
+        HostPipeline(m)                               # the serving pipeline has no CPU path either
+    with pytest.raises(ValueError):
+        HostPipeline(m, depth=1)
     bad = _lib.FvConfig()
     bad.kind = 17
     h = C.c_void_p()
