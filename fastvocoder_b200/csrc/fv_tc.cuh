@@ -1305,6 +1305,14 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   }
   struct Cand { int mt, a_st, res, w_st, ck, kbps, dual; double score; };
   Cand best{0, 0, 0, 0, 0, 0, 0, -1.0};
+  Cand best2{0, 0, 0, 0, 0, 0, 0, -1.0};   // best candidate with TWO accumulator sets
+  // Upsample layers (phase-interleaved outputs) are bound by their epilogue: with a single accumulator set the MMAs of the next
+  // tile wait for it (issuer 62-86 % in acc_empty, epilogue 21-32 % in acc_full, profiles/r02_stall_hifigan_b32.txt), and the
+  // cycle model underrates that.  Measured in one call (gpurun r2ab, FV_TC2_MT_XS=1): 256 -> 8 x 128: 0.205 -> 0.140 ms,
+  // 64 -> 3 x 32: 0.277 -> 0.222 ms with one M tile and two sets -> those layouts take the best two-set plan when there is one.
+  // The M-tile count does not change the accumulation order (ck does), so results are unchanged.  FV_TC2_UPS_ACC2=0: off.
+  static const bool ups_acc2_env = getenv("FV_TC2_UPS_ACC2") == nullptr || atoi(getenv("FV_TC2_UPS_ACC2")) != 0;
+  const bool prefer_acc2 = ups_acc2_env && (a.out_layout == OUT_PHASE || a.out_layout == OUT_PHASE_SPLIT);
   // Cycle model per CTA tile, calibrated on B200 (profiles/r01_notes.md, scripts/probes/umma_issue_probe.cu and the
   // FV_STALL_DEBUG role accounting):
   //   UMMA M=128 K=16: max(N/2, (4096 + 32 N)/128) clk — math vs the 128 B/clk shared-memory operand fetch; a tight
@@ -1325,6 +1333,7 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
   const int pl_B = phase == 0 ? 8 : a.B;
   const int need_mt = (pl_Lpos + 127) / 128;
   best = Cand{0, 0, 0, 0, 0, 0, 0, -1.0};
+  best2 = Cand{0, 0, 0, 0, 0, 0, 0, -1.0};
   for (int df = 2; df >= 1; --df) {
     if (df == 2 && NT > 128) continue;
     if (force_dual >= 0 && NT <= 128 && (df == 2) != (force_dual != 0)) continue;
@@ -1385,11 +1394,13 @@ inline bool tc2_plan(const ConvArgs& a, const TcLayer& L, Tc2Args& p, int num_sm
               const double useful = std::min<double>(mt * 128.0, (double)pl_Lpos);
               const double sc = useful / t_tile * tail_eff;
               if (sc > best.score * 1.02) best = Cand{mt, a_st, res, w_st, ck, kbps, df, sc};
+              if (acc2 && sc > best2.score * 1.02) best2 = Cand{mt, a_st, res, w_st, ck, kbps, df, sc};
             }
           }
     }
   }
   if (best.score < 0) return false;
+  if (prefer_acc2 && best2.score > 0) best = best2;
   ck_fixed = best.ck;
   }   // phase
   const int dualf = best.dual;
@@ -2382,8 +2393,10 @@ retry:
   // 3 = every resident unit
   static const int pp_env = getenv("FV_TC3_PP") ? atoi(getenv("FV_TC3_PP")) : 2;
   // split (TMA-fed) units at C = 16: ping-pong tiles also for k = 3 (m 3 -> 8: eight independent accumulator chains per
-  // tile keep the tensor pipe fed, profiles/r02_notes.md: 311 -> 276 kclk); C = 32 k = 3 measured neutral (294 vs 297)
-  if (best_sc >= 0 && (pp_env >= 3 || (pp_env == 2 && (K >= 7 || (split && C <= 16))))) {
+  // tile keep the tensor pipe fed, profiles/r02_notes.md: 311 -> 276 kclk); C = 32 k = 3 measured neutral then (294 vs 297 kclk, before the second epiB group)
+  // re-measured on the final binary (gpurun r2ab, FV_TC3_PP=3): C = 32 k = 3 1.109-1.125 -> 1.015 ms per three units (m 2 -> 4: four
+  // accumulator chains per tile instead of two; the issuers of the m = 2 plan sat 91 % busy at ~210 clk per dependent UMMA)
+  if (best_sc >= 0 && (pp_env >= 3 || (pp_env == 2 && (K >= 7 || (split && C <= 32))))) {
     // Resident weights + ping-pong tiles: the same two tiles in flight need half the TMEM and no A2 buffer, so the tile can be
     // taller (C=32: m 2 -> 4, C=16: m 3-4 -> 8): less conv2 halo recompute and fewer per-tile hand-offs.  Measured in one call
     // (gpurun_out/pp2_*): C=32 k=11 0.676 -> 0.60 ms, C=16 k=11 0.61 -> 0.52, k=7 -3 %, k=3 +-3 % (left on the old plans);
