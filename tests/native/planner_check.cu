@@ -44,6 +44,10 @@ static int check_tc2(int B, int Cin, int N, int K, int dil, int L, bool res, int
   CHECK(p.ld_per >= 0 && p.ld_per <= LD_MAX, "ld_per=%d", p.ld_per);
   CHECK(!p.dual || 2 * p.NT <= 256, "dual N");
   CHECK(p.total_tiles == p.tiles_per_batch * B && p.tiles_per_batch * p.m_tiles * 128 >= L, "tiles");
+  // upsample (phase-interleaved) layers are epilogue-bound: they must get two accumulator sets whenever one M tile fits twice
+  if (layout == OUT_PHASE && !getenv("FV_TC2_UPS_ACC2"))
+    CHECK(p.acc_stages == 2 || 2 * p.NT * (p.dual ? 2 : 1) > 512, "upsample plan with one accumulator set: NT=%d mt=%d dual=%d", p.NT,
+          p.m_tiles, p.dual);
   return 1;
 }
 
